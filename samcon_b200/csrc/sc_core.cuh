@@ -1,0 +1,922 @@
+// sc_core.cuh -- per-sample humanoid rollout, written as "lane stages".
+//
+// Mapping: one sample is owned by a QUAD of 4 lanes; a warp carries a TILE of 8 samples.
+// lane = slot*8 + s  (s = sample in tile 0..7, slot = 0..3).  Bodies are numbered level by level and no tree
+// level is wider than 4, so in every tree sweep the quad's lane `slot` owns body level_start[d]+slot.
+// All per-sample working data lives in shared memory, interleaved so that word w of sample s sits at
+// sm[w*8+s] (the 8 samples of a tile hit 8 different banks; the <=4 bodies of a level have consecutive ids).
+// A "stage" is a piece of straight-line per-lane code followed by a warp barrier; no per-lane value lives
+// across a barrier.  That discipline lets the same source be compiled for the host as a lane loop
+// (tests/emu, debugging aid only -- the package never loads it) and for sm_100a with __syncwarp().
+//
+// Arithmetic follows the reference call chain env.step -> actuate -> stepSimulation -> cost
+// (/root/reference/envs/humanoid_tracking_env.py:184-200, humanoid_stable_pd.py:124-135) as restated in
+// DESIGN.md §2; algorithms: articulated-body recursion specialised to spherical joints about the joint
+// centre (S=[1;0]), stable PD as an ABA with joint armature dt*Kd, contact-space Gauss-Seidel.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include "../../include/samcon_b200.h"
+
+#if defined(__CUDACC__)
+#define SC_DEV __device__ __forceinline__
+#define SC_SYNC() __syncwarp()
+#else
+#define SC_DEV static inline
+#define SC_SYNC() ((void)0)
+#endif
+
+namespace sc {
+
+constexpr int NB = SC_MAX_BODIES;
+constexpr int MAXLEV = SC_MAX_LEVELS;
+constexpr int MAXC = SC_MAX_CONTACTS;
+constexpr int NR = 3 * MAXC;
+constexpr int TILE = 8;   // samples per warp
+constexpr int QUAD = 4;   // lanes per sample
+
+// ---- derived model tables (copied to shared memory once per CTA) ------------------------------------------
+struct Tables {
+    int nb, nlev, ncand, ncp, nee, niter, nsub, maxc, nj;
+    int parent[NB], depth[NB], jidx[NB], jbody[NB], nchild[NB], child[NB][4], level_start[MAXLEV + 1], anc_mask[NB];
+    int cand_body[SC_MAX_CAND], cp_body[SC_MAX_CPOINTS], ee[4];
+    float jorg[NB * 3], idyn[NB * 10], ipd[NB * 10], kp[NB], kd[NB], maxf[NB], cand[SC_MAX_CAND * 4];
+    float cp_off[SC_MAX_CPOINTS * 3], cp_mass[SC_MAX_CPOINTS], jw[NB], cw[5];
+    float height, dt, h, g[3], mu, erp, cthresh, maxvel, inv_total_mass;
+};
+
+// ---- per-sample shared-memory layout (32-bit words) --------------------------------------------------------
+constexpr int O_P0 = 0;                   // root position (3)
+constexpr int O_Q = O_P0 + 3;             // quaternions xyzw: body 0 = root orientation, b>0 = joint rotation
+constexpr int O_VB = O_Q + 4 * NB;        // base world velocity: angular(3), linear(3)
+constexpr int O_W = O_VB + 6;             // joint angular velocity in child frame (3 per body, slot 0 unused)
+constexpr int O_RW = O_W + 3 * NB;        // world rotation per body (9)
+constexpr int O_PW = O_RW + 9 * NB;       // world position of body origin (3)
+constexpr int O_TW = O_PW + 3 * NB;       // body twist in body coords: ang(3), lin(3)
+constexpr int O_TAU = O_TW + 6 * NB;      // joint torque held over the sub-steps (3)
+constexpr int O_IC = O_TAU + 3 * NB;      // articulated-inertia contribution to the parent: A(6) B(9) C(6)
+constexpr int O_PC = O_IC + 21 * NB;      // bias-force contribution to the parent (6); later: accelerations
+constexpr int O_UA = O_PC + 6 * NB;       // articulated inertia, angular block (sym 6)
+constexpr int O_UB = O_UA + 6 * NB;       // articulated inertia, linear-from-angular block (9)
+constexpr int O_DI = O_UB + 9 * NB;       // (S^T IA S + armature)^-1 (sym 6)
+constexpr int O_UU = O_DI + 6 * NB;       // u = tau - S^T pA (3)
+constexpr int O_I0L = O_UU + 3 * NB;      // Cholesky factor of the base articulated inertia (21)
+constexpr int O_TP = O_I0L + 21;          // PD: Kp*err - Kd*w (3); contact apply: -S^T pa (3)
+constexpr int O_CB = O_TP + 3 * NB;       // contact body (int)
+constexpr int O_CR = O_CB + MAXC;         // contact point relative to body origin, body coords (3)
+constexpr int O_CD = O_CR + 3 * MAXC;     // signed distance
+constexpr int O_NC = O_CD + MAXC;         // number of contacts (int)
+constexpr int O_TM = O_NC + 1;            // mask of bodies on a root path of some contact (int)
+constexpr int O_DU = O_TM + 1;            // response pass: u per chain level, 3 columns (9 per level)
+constexpr int O_AM = O_DU + 9 * MAXLEV;   // contact-space matrix, packed lower triangle
+constexpr int O_RHS = O_AM + NR * (NR + 1) / 2;
+constexpr int O_LAM = O_RHS + NR;
+constexpr int O_RES = O_LAM + NR;
+constexpr int O_DGI = O_RES + NR;
+constexpr int O_DEL = O_DGI + NR;         // pending impulse change, double buffered (2)
+constexpr int O_FEAT = O_DEL + 2;         // com(3) comvel(3) ee(4x3)
+constexpr int O_END = O_FEAT + 18;
+constexpr int O_DA = O_IC;                // response pass: accelerations, 3 columns x 6 per body (aliases IC)
+constexpr int O_ZC = O_AM;                // collide: candidate heights (aliases AM)
+static_assert(18 * NB <= 21 * NB, "DA must fit in IC");
+static_assert(SC_MAX_CAND <= NR * (NR + 1) / 2, "ZC must fit in AM");
+constexpr int WORDS_PER_SAMPLE = O_END;
+constexpr int WORDS_PER_TILE = WORDS_PER_SAMPLE * TILE;
+
+#define F(i) S[(i) * sc::TILE]
+
+SC_DEV int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+SC_DEV float i2f(int i) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+SC_DEV float rsq(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+// ---- small vector algebra in registers -------------------------------------------------------------------
+struct V3 { float x, y, z; };
+struct M3 { float a[9]; };            // row major
+struct S3 { float xx, xy, xz, yy, yz, zz; };
+
+SC_DEV V3 mk(float x, float y, float z) { V3 v = {x, y, z}; return v; }
+SC_DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+SC_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+SC_DEV V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+SC_DEV V3 neg(V3 a) { return mk(-a.x, -a.y, -a.z); }
+SC_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+SC_DEV V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+SC_DEV V3 mul(const M3 &R, V3 v) {
+    return mk(R.a[0] * v.x + R.a[1] * v.y + R.a[2] * v.z, R.a[3] * v.x + R.a[4] * v.y + R.a[5] * v.z,
+              R.a[6] * v.x + R.a[7] * v.y + R.a[8] * v.z);
+}
+SC_DEV V3 mulT(const M3 &R, V3 v) {
+    return mk(R.a[0] * v.x + R.a[3] * v.y + R.a[6] * v.z, R.a[1] * v.x + R.a[4] * v.y + R.a[7] * v.z,
+              R.a[2] * v.x + R.a[5] * v.y + R.a[8] * v.z);
+}
+SC_DEV V3 mul(const S3 &A, V3 v) {
+    return mk(A.xx * v.x + A.xy * v.y + A.xz * v.z, A.xy * v.x + A.yy * v.y + A.yz * v.z,
+              A.xz * v.x + A.yz * v.y + A.zz * v.z);
+}
+SC_DEV M3 mul(const M3 &A, const M3 &B) {
+    M3 C;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) C.a[3 * i + j] = A.a[3 * i] * B.a[j] + A.a[3 * i + 1] * B.a[3 + j] + A.a[3 * i + 2] * B.a[6 + j];
+    return C;
+}
+SC_DEV M3 mulBt(const M3 &A, const M3 &B) {  // A * B^T
+    M3 C;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) C.a[3 * i + j] = A.a[3 * i] * B.a[3 * j] + A.a[3 * i + 1] * B.a[3 * j + 1] + A.a[3 * i + 2] * B.a[3 * j + 2];
+    return C;
+}
+SC_DEV M3 tom(const S3 &A) { M3 M = {{A.xx, A.xy, A.xz, A.xy, A.yy, A.yz, A.xz, A.yz, A.zz}}; return M; }
+SC_DEV S3 upper(const M3 &M) { S3 A = {M.a[0], M.a[1], M.a[2], M.a[4], M.a[5], M.a[8]}; return A; }
+SC_DEV V3 row(const M3 &M, int i) { return mk(M.a[3 * i], M.a[3 * i + 1], M.a[3 * i + 2]); }
+SC_DEV V3 col(const M3 &M, int j) { return mk(M.a[j], M.a[3 + j], M.a[6 + j]); }
+SC_DEV void setrow(M3 &M, int i, V3 v) { M.a[3 * i] = v.x; M.a[3 * i + 1] = v.y; M.a[3 * i + 2] = v.z; }
+SC_DEV void setcol(M3 &M, int j, V3 v) { M.a[j] = v.x; M.a[3 + j] = v.y; M.a[6 + j] = v.z; }
+SC_DEV S3 inv(const S3 &A) {
+    float c0 = A.yy * A.zz - A.yz * A.yz, c1 = A.xz * A.yz - A.xy * A.zz, c2 = A.xy * A.yz - A.xz * A.yy;
+    float id = 1.0f / (A.xx * c0 + A.xy * c1 + A.xz * c2);
+    S3 K = {c0 * id, c1 * id, c2 * id, (A.xx * A.zz - A.xz * A.xz) * id, (A.xz * A.xy - A.xx * A.yz) * id,
+            (A.xx * A.yy - A.xy * A.xy) * id};
+    return K;
+}
+SC_DEV M3 quat2R(float x, float y, float z, float w) {
+    M3 R = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z),
+             2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
+    return R;
+}
+// rotate a symmetric / general 3x3 block: R M R^T
+SC_DEV M3 rot(const M3 &R, const M3 &M) { return mulBt(mul(R, M), R); }
+
+// ---- shared-memory load/store helpers ----------------------------------------------------------------------
+SC_DEV V3 ld3(const float *S, int o) { return mk(F(o), F(o + 1), F(o + 2)); }
+SC_DEV void st3(float *S, int o, V3 v) { F(o) = v.x; F(o + 1) = v.y; F(o + 2) = v.z; }
+SC_DEV M3 ldM(const float *S, int o) {
+    M3 M;
+#pragma unroll
+    for (int i = 0; i < 9; i++) M.a[i] = F(o + i);
+    return M;
+}
+SC_DEV void stM(float *S, int o, const M3 &M) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) F(o + i) = M.a[i];
+}
+SC_DEV S3 ldS(const float *S, int o) { S3 A = {F(o), F(o + 1), F(o + 2), F(o + 3), F(o + 4), F(o + 5)}; return A; }
+SC_DEV void stS(float *S, int o, const S3 &A) {
+    F(o) = A.xx; F(o + 1) = A.xy; F(o + 2) = A.xz; F(o + 3) = A.yy; F(o + 4) = A.yz; F(o + 5) = A.zz;
+}
+SC_DEV M3 ldRj(const float *S, int b) { return quat2R(F(O_Q + 4 * b), F(O_Q + 4 * b + 1), F(O_Q + 4 * b + 2), F(O_Q + 4 * b + 3)); }
+SC_DEV V3 tv3(const float *t, int i) { return mk(t[3 * i], t[3 * i + 1], t[3 * i + 2]); }
+
+// 6x6 SPD solve, packed lower triangle, diagonal stored inverted
+SC_DEV constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+SC_DEV void chol6(float *a) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        float d = a[tri(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= a[tri(j, k)] * a[tri(j, k)];
+        float id = rsq(d);
+        a[tri(j, j)] = id;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            float s = a[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= a[tri(i, k)] * a[tri(j, k)];
+            a[tri(i, j)] = s * id;
+        }
+    }
+}
+SC_DEV void solve6(const float *L, float *x) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float s = x[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= L[tri(i, k)] * x[k];
+        x[i] = s * L[tri(i, i)];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        float s = x[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) s -= L[tri(k, i)] * x[k];
+        x[i] = s * L[tri(i, i)];
+    }
+}
+
+// max over the 8 samples of a tile of an int field; call between stages only
+SC_DEV int tile_max_int(const float *sm, int off) {
+#if defined(__CUDA_ARCH__)
+    int v = f2i(sm[off * TILE + (threadIdx.x & 7)]);
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    return v;
+#else
+    int v = f2i(sm[off * TILE]);
+    for (int s = 1; s < TILE; s++) { int u = f2i(sm[off * TILE + s]); v = u > v ? u : v; }
+    return v;
+#endif
+}
+
+#define SC_STAGE for (int lane = L0; lane < L1; ++lane)
+#define SC_LANE float *S = sm + (lane & 7); const int slot = lane >> 3; (void)slot; (void)S
+
+// ============================================================================================================
+// kinematics
+// ============================================================================================================
+SC_DEV void fk_body(float *S, const Tables &T, int b, bool full) {
+    if (b == 0) {
+        M3 R = ldRj(S, 0);
+        if (full) { stM(S, O_RW, R); st3(S, O_PW, ld3(S, O_P0)); }
+        st3(S, O_TW, mulT(R, ld3(S, O_VB)));
+        st3(S, O_TW + 3, mulT(R, ld3(S, O_VB + 3)));
+    } else {
+        const int p = T.parent[b];
+        M3 Rj = ldRj(S, b);
+        V3 r = tv3(T.jorg, b);
+        if (full) {
+            M3 Rp = ldM(S, O_RW + 9 * p);
+            stM(S, O_RW + 9 * b, mul(Rp, Rj));
+            st3(S, O_PW + 3 * b, ld3(S, O_PW + 3 * p) + mul(Rp, r));
+        }
+        V3 wp = ld3(S, O_TW + 6 * p), vp = ld3(S, O_TW + 6 * p + 3);
+        st3(S, O_TW + 6 * b, mulT(Rj, wp) + ld3(S, O_W + 3 * b));
+        st3(S, O_TW + 6 * b + 3, mulT(Rj, vp + cross(wp, r)));
+    }
+}
+
+template <class TT>
+SC_DEV void fk_sweep(float *sm, const TT &T, int L0, int L1, bool full) {
+    for (int d = 0; d < T.nlev; d++) {
+        SC_STAGE {
+            SC_LANE;
+            int b = T.level_start[d] + slot;
+            if (b < T.level_start[d + 1]) fk_body(S, T, b, full);
+        }
+        SC_SYNC();
+    }
+}
+
+// ============================================================================================================
+// articulated-body algorithm (PD = stable-PD variant: pd inertia set, armature dt*Kd, torque from O_TP)
+// ============================================================================================================
+template <bool PD>
+SC_DEV void aba_backward_body(float *S, const Tables &T, int b) {
+    const float *I = (PD ? T.ipd : T.idyn) + 10 * b;
+    const float m = I[0];
+    const V3 hh = mk(I[1], I[2], I[3]);
+    S3 A = {I[4], I[5], I[6], I[7], I[8], I[9]};
+    M3 B = {{0, hh.z, -hh.y, -hh.z, 0, hh.x, hh.y, -hh.x, 0}};   // -skew(h)
+    S3 C = {m, 0, 0, m, 0, m};
+    const V3 w = ld3(S, O_TW + 6 * b), v = ld3(S, O_TW + 6 * b + 3);
+    // own bias force v x* (I v)
+    V3 n0 = mul(A, w) + cross(hh, v);
+    V3 f0 = m * v - cross(hh, w);
+    V3 pn = cross(w, n0) + cross(v, f0);
+    V3 pf = cross(w, f0);
+    for (int k = 0; k < T.nchild[b]; k++) {
+        const int c = T.child[b][k];
+        const int o = O_IC + 21 * c;
+        A.xx += F(o); A.xy += F(o + 1); A.xz += F(o + 2); A.yy += F(o + 3); A.yz += F(o + 4); A.zz += F(o + 5);
+#pragma unroll
+        for (int i = 0; i < 9; i++) B.a[i] += F(o + 6 + i);
+        C.xx += F(o + 15); C.xy += F(o + 16); C.xz += F(o + 17); C.yy += F(o + 18); C.yz += F(o + 19); C.zz += F(o + 20);
+        pn = pn + ld3(S, O_PC + 6 * c);
+        pf = pf + ld3(S, O_PC + 6 * c + 3);
+    }
+    if (b == 0) {
+        // floating base: a0 = -IA^-1 pA in the free-fall frame; gravity is added when velocities are updated
+        float L[21] = {A.xx, A.xy, A.yy, A.xz, A.yz, A.zz,
+                       B.a[0], B.a[1], B.a[2], C.xx,
+                       B.a[3], B.a[4], B.a[5], C.xy, C.yy,
+                       B.a[6], B.a[7], B.a[8], C.xz, C.yz, C.zz};
+        chol6(L);
+        float x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
+        solve6(L, x);
+#pragma unroll
+        for (int i = 0; i < 21; i++) F(O_I0L + i) = L[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) F(O_PC + i) = x[i];
+        if (!PD) {
+            // world-frame base velocity update: w += h R alpha ; v += h (R (a + w x v) + g)
+            M3 R = ldM(S, O_RW);
+            V3 al = mk(x[0], x[1], x[2]), a = mk(x[3], x[4], x[5]) + cross(w, v);
+            V3 dw = mul(R, al), dv = mul(R, a);
+            F(O_VB) += T.h * dw.x; F(O_VB + 1) += T.h * dw.y; F(O_VB + 2) += T.h * dw.z;
+            F(O_VB + 3) += T.h * (dv.x + T.g[0]); F(O_VB + 4) += T.h * (dv.y + T.g[1]); F(O_VB + 5) += T.h * (dv.z + T.g[2]);
+        }
+        return;
+    }
+    const float arm = PD ? T.dt * T.kd[b] : 0.0f;
+    S3 D = A; D.xx += arm; D.yy += arm; D.zz += arm;
+    const S3 K = inv(D);
+    const V3 tau = ld3(S, (PD ? O_TP : O_TAU) + 3 * b);
+    const V3 u = tau - pn;
+    const V3 wj = ld3(S, O_W + 3 * b);
+    const V3 cw = cross(w, wj), cv = cross(v, wj);
+    stS(S, O_UA + 6 * b, A); stM(S, O_UB + 9 * b, B); stS(S, O_DI + 6 * b, K); st3(S, O_UU + 3 * b, u);
+    const M3 Am = tom(A), Km = tom(K);
+    const M3 AK = mul(Am, Km), BK = mul(B, Km);
+    const M3 AKA = mul(AK, Am), BKA = mul(BK, Am), BKB = mulBt(BK, B);
+    M3 Aa, Ba, Ca;
+    const M3 Cm = tom(C);
+#pragma unroll
+    for (int i = 0; i < 9; i++) { Aa.a[i] = Am.a[i] - AKA.a[i]; Ba.a[i] = B.a[i] - BKA.a[i]; Ca.a[i] = Cm.a[i] - BKB.a[i]; }
+    const V3 Ku = mul(K, u);
+    V3 pan = pn + mul(Aa, cw) + mulT(Ba, cv) + mul(A, Ku);
+    V3 paf = pf + mul(Ba, cw) + mul(Ca, cv) + mul(B, Ku);
+    // to parent coordinates: rotate by Rj, then shift the reference point by r
+    const M3 Rj = ldRj(S, b);
+    const V3 r = tv3(T.jorg, b);
+    const M3 A1 = rot(Rj, Aa), B1 = rot(Rj, Ba), C1 = rot(Rj, Ca);
+    M3 CR, Bp, Ap;
+#pragma unroll
+    for (int i = 0; i < 3; i++) setrow(CR, i, cross(row(C1, i), r));              // C1 * rx
+#pragma unroll
+    for (int i = 0; i < 9; i++) Bp.a[i] = B1.a[i] - CR.a[i];
+    // Ap = A1 - B1^T rx + rx B1 - rx C1 rx = A1 - B1^T rx + rx Bp
+    M3 BtR, RB;
+#pragma unroll
+    for (int i = 0; i < 3; i++) setrow(BtR, i, cross(col(B1, i), r));             // B1^T * rx
+#pragma unroll
+    for (int j = 0; j < 3; j++) setcol(RB, j, cross(r, col(Bp, j)));              // rx * Bp
+#pragma unroll
+    for (int i = 0; i < 9; i++) Ap.a[i] = A1.a[i] - BtR.a[i] + RB.a[i];
+    const int o = O_IC + 21 * b;
+    stS(S, o, upper(Ap)); stM(S, o + 6, Bp); stS(S, o + 15, upper(C1));
+    const V3 fp = mul(Rj, paf);
+    st3(S, O_PC + 6 * b, mul(Rj, pan) + cross(r, fp));
+    st3(S, O_PC + 6 * b + 3, fp);
+}
+
+template <bool PD>
+SC_DEV void aba_forward_body(float *S, const Tables &T, int b) {
+    const int p = T.parent[b];
+    const M3 Rj = ldRj(S, b);
+    const V3 r = tv3(T.jorg, b);
+    const V3 alp = ld3(S, O_PC + 6 * p), ap = ld3(S, O_PC + 6 * p + 3);
+    const V3 w = ld3(S, O_TW + 6 * b), v = ld3(S, O_TW + 6 * b + 3), wj = ld3(S, O_W + 3 * b);
+    const V3 aw = mulT(Rj, alp) + cross(w, wj);
+    const V3 al = mulT(Rj, ap + cross(alp, r)) + cross(v, wj);
+    const S3 A = ldS(S, O_UA + 6 * b), K = ldS(S, O_DI + 6 * b);
+    const M3 B = ldM(S, O_UB + 9 * b);
+    const V3 qdd = mul(K, ld3(S, O_UU + 3 * b) - mul(A, aw) - mulT(B, al));
+    st3(S, O_PC + 6 * b, aw + qdd);
+    st3(S, O_PC + 6 * b + 3, al);
+    if (PD) {
+        // tau = Kp err - Kd (w + dt qdd), clamped per axis (humanoid_stable_pd.py:52-59 max_forces)
+        const float kd = T.dt * T.kd[b], mf = T.maxf[b];
+        V3 t = ld3(S, O_TP + 3 * b) - kd * qdd;
+        st3(S, O_TAU + 3 * b, mk(fminf(mf, fmaxf(-mf, t.x)), fminf(mf, fmaxf(-mf, t.y)), fminf(mf, fmaxf(-mf, t.z))));
+    } else {
+        st3(S, O_W + 3 * b, wj + T.h * qdd);
+    }
+}
+
+template <bool PD, class TT>
+SC_DEV void aba(float *sm, const TT &T, int L0, int L1) {
+    for (int d = T.nlev - 1; d >= 0; d--) {
+        SC_STAGE {
+            SC_LANE;
+            int b = T.level_start[d] + slot;
+            if (b < T.level_start[d + 1]) aba_backward_body<PD>(S, T, b);
+        }
+        SC_SYNC();
+    }
+    for (int d = 1; d < T.nlev; d++) {
+        SC_STAGE {
+            SC_LANE;
+            int b = T.level_start[d] + slot;
+            if (b < T.level_start[d + 1]) aba_forward_body<PD>(S, T, b);
+        }
+        SC_SYNC();
+    }
+}
+
+// stable-PD proportional/derivative term: Kp * log(q_pred^-1 q_target) - Kd * w   
+SC_DEV void pd_term_body(float *S, const Tables &T, int b, const float *act) {
+    const float qx = F(O_Q + 4 * b), qy = F(O_Q + 4 * b + 1), qz = F(O_Q + 4 * b + 2), qw = F(O_Q + 4 * b + 3);
+    const V3 w = ld3(S, O_W + 3 * b);
+    const float hd = 0.5f * T.dt;
+    // q_pred = normalize(q + dt/2 * q (x) (w,0))
+    float px = qx + hd * (qw * w.x + qy * w.z - qz * w.y);
+    float py = qy + hd * (qw * w.y - qx * w.z + qz * w.x);
+    float pz = qz + hd * (qw * w.z + qx * w.y - qy * w.x);
+    float pw = qw + hd * (-qx * w.x - qy * w.y - qz * w.z);
+    const float *t = act + 4 * T.jidx[b];
+    float tx = t[0], ty = t[1], tz = t[2], tw = t[3];
+    // d = conj(p) (x) t   (scale of p and t is irrelevant for the axis, and removed for the angle by atan2)
+    float dx = pw * tx - px * tw - py * tz + pz * ty;
+    float dy = pw * ty + px * tz - py * tw - pz * tx;
+    float dz = pw * tz - px * ty + py * tx - pz * tw;
+    float dw = pw * tw + px * tx + py * ty + pz * tz;
+    if (dw < 0) { dx = -dx; dy = -dy; dz = -dz; dw = -dw; }
+    float s = sqrtf(dx * dx + dy * dy + dz * dz);
+    float k = s > 1e-12f ? 2.0f * atan2f(s, dw) / s : 0.0f;
+    const float kp = T.kp[b], kd = T.kd[b];
+    st3(S, O_TP + 3 * b, mk(kp * k * dx - kd * w.x, kp * k * dy - kd * w.y, kp * k * dz - kd * w.z));
+}
+
+// ============================================================================================================
+// ground contact
+// ============================================================================================================
+// unit direction k of the contact frame in the coordinates of a body with world rotation R:
+// n = +z, t1 = -y, t2 = +x (Bullet's btPlaneSpace1 of the plane normal)
+SC_DEV V3 cdir(const M3 &R, int k) { return k == 0 ? row(R, 2) : (k == 1 ? neg(row(R, 1)) : row(R, 0)); }
+SC_DEV float cproj(V3 w, int k) { return k == 0 ? w.z : (k == 1 ? -w.y : w.x); }
+
+template <class TT>
+SC_DEV void collide(float *sm, const TT &T, int L0, int L1) {
+    SC_STAGE {
+        SC_LANE;
+        for (int c = slot; c < T.ncand; c += QUAD) {
+            const int b = T.cand_body[c];
+            const float *pt = T.cand + 4 * c;
+            F(O_ZC + c) = F(O_PW + 3 * b + 2) + F(O_RW + 9 * b + 6) * pt[0] + F(O_RW + 9 * b + 7) * pt[1] +
+                          F(O_RW + 9 * b + 8) * pt[2] - pt[3];
+        }
+    }
+    SC_SYNC();
+    SC_STAGE {
+        SC_LANE;
+        if (slot == 0) {
+            // O_CB holds candidate indices and O_CD heights while the deepest maxc are being chosen
+            int n = 0;
+            for (int c = 0; c < T.ncand; c++) {
+                const float z = F(O_ZC + c);
+                if (!(z < T.cthresh)) continue;
+                if (n < T.maxc) { F(O_CB + n) = i2f(c); F(O_CD + n) = z; n++; continue; }
+                int worst = 0;
+                float zw = F(O_CD);
+                for (int j = 1; j < n; j++) { const float zj = F(O_CD + j); if (zj >= zw) { worst = j; zw = zj; } }
+                if (z < zw) {
+                    for (int j = worst; j + 1 < n; j++) { F(O_CB + j) = F(O_CB + j + 1); F(O_CD + j) = F(O_CD + j + 1); }
+                    F(O_CB + n - 1) = i2f(c); F(O_CD + n - 1) = z;
+                }
+            }
+            int mask = 0;
+            for (int j = 0; j < n; j++) {
+                const int c = f2i(F(O_CB + j)), b = T.cand_body[c];
+                const float *pt = T.cand + 4 * c;
+                F(O_CB + j) = i2f(b);
+                F(O_CR + 3 * j) = pt[0] - pt[3] * F(O_RW + 9 * b + 6);
+                F(O_CR + 3 * j + 1) = pt[1] - pt[3] * F(O_RW + 9 * b + 7);
+                F(O_CR + 3 * j + 2) = pt[2] - pt[3] * F(O_RW + 9 * b + 8);
+                mask |= T.anc_mask[b];
+            }
+            F(O_NC) = i2f(n);
+            F(O_TM) = i2f(mask);
+        }
+    }
+    SC_SYNC();
+}
+
+// one column of the articulated response: walk a spatial force on `b` (body coords) up to the root,
+// recording u per level, and solve the base.  Runs inside one lane (no barrier needed).
+SC_DEV void response_chain(float *S, const Tables &T, int b, V3 n, V3 f, int colofs_u, int colofs_a) {
+    V3 pn = neg(n), pf = neg(f);
+    while (b != 0) {
+        const V3 u = neg(pn);
+        st3(S, O_DU + 9 * T.depth[b] + colofs_u, u);
+        const V3 Ku = mul(ldS(S, O_DI + 6 * b), u);
+        pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
+        pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
+        const M3 Rj = ldRj(S, b);
+        const V3 fp = mul(Rj, pf);
+        pn = mul(Rj, pn) + cross(tv3(T.jorg, b), fp);
+        pf = fp;
+        b = T.parent[b];
+    }
+    float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
+#pragma unroll
+    for (int i = 0; i < 21; i++) L[i] = F(O_I0L + i);
+    solve6(L, x);
+#pragma unroll
+    for (int i = 0; i < 6; i++) F(O_DA + colofs_a + i) = x[i];
+}
+
+template <class TT>
+SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax) {
+    // ---- right-hand sides from the predicted velocities -----------------------------------------------------
+    SC_STAGE {
+        SC_LANE;
+        const int nc = f2i(F(O_NC));
+        for (int j = slot; j < nc; j += QUAD) {
+            const int b = f2i(F(O_CB + j));
+            const V3 rl = ld3(S, O_CR + 3 * j);
+            const V3 vp = mul(ldM(S, O_RW + 9 * b), ld3(S, O_TW + 6 * b + 3) + cross(ld3(S, O_TW + 6 * b), rl));
+            const float dist = F(O_CD + j);
+            F(O_RHS + 3 * j) = -vp.z - (dist > 0 ? dist / T.h : dist * T.erp / T.h);
+            F(O_RHS + 3 * j + 1) = vp.y;
+            F(O_RHS + 3 * j + 2) = -vp.x;
+            F(O_LAM + 3 * j) = 0; F(O_LAM + 3 * j + 1) = 0; F(O_LAM + 3 * j + 2) = 0;
+        }
+        if (slot == 0) { F(O_DEL) = 0; F(O_DEL + 1) = 0; }
+    }
+    SC_SYNC();
+    // ---- contact-space matrix, one contact (3 columns) at a time ----------------------------------------------
+    for (int j = 0; j < ncmax; j++) {
+        SC_STAGE {
+            SC_LANE;
+            const int nc = f2i(F(O_NC));
+            if (j < nc && slot < 3) {
+                const int b = f2i(F(O_CB + j));
+                const V3 f = cdir(ldM(S, O_RW + 9 * b), slot);
+                response_chain(S, T, b, cross(ld3(S, O_CR + 3 * j), f), f, 3 * slot, 6 * slot);
+            }
+        }
+        SC_SYNC();
+        for (int d = 1; d < T.nlev; d++) {
+            SC_STAGE {
+                SC_LANE;
+                const int nc = f2i(F(O_NC));
+                if (j < nc) {
+                    const int mask = f2i(F(O_TM)), chain = T.anc_mask[f2i(F(O_CB + j))];
+                    const int width = T.level_start[d + 1] - T.level_start[d];
+                    for (int it = slot; it < 3 * width; it += QUAD) {
+                        const int b = T.level_start[d] + it / 3, c = it % 3;
+                        if (!((mask >> b) & 1)) continue;
+                        const int p = T.parent[b];
+                        const M3 Rj = ldRj(S, b);
+                        const V3 alp = ld3(S, O_DA + 18 * p + 6 * c), ap = ld3(S, O_DA + 18 * p + 6 * c + 3);
+                        const V3 aw = mulT(Rj, alp), al = mulT(Rj, ap + cross(alp, tv3(T.jorg, b)));
+                        V3 u = mk(0, 0, 0);
+                        if ((chain >> b) & 1) u = ld3(S, O_DU + 9 * d + 3 * c);
+                        const V3 qdd = mul(ldS(S, O_DI + 6 * b), u - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
+                        st3(S, O_DA + 18 * b + 6 * c, aw + qdd);
+                        st3(S, O_DA + 18 * b + 6 * c + 3, al);
+                    }
+                }
+            }
+            SC_SYNC();
+        }
+        SC_STAGE {
+            SC_LANE;
+            const int nc = f2i(F(O_NC));
+            if (j < nc) {
+                for (int it = 3 * j + slot; it < 3 * nc; it += QUAD) {
+                    const int i = it / 3, c = it % 3;
+                    const int b = f2i(F(O_CB + i));
+                    const V3 a = ld3(S, O_DA + 18 * b + 6 * c + 3) + cross(ld3(S, O_DA + 18 * b + 6 * c), ld3(S, O_CR + 3 * i));
+                    const V3 aw = mul(ldM(S, O_RW + 9 * b), a);
+                    const int cc = 3 * j + c;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const int rr = 3 * i + k;
+                        if (rr >= cc) F(O_AM + rr * (rr + 1) / 2 + cc) = cproj(aw, k);
+                    }
+                }
+            }
+        }
+        SC_SYNC();
+    }
+    // ---- projected Gauss-Seidel, Bullet row order: all normals, then the friction pairs -------------------------
+    SC_STAGE {
+        SC_LANE;
+        const int nc = f2i(F(O_NC));
+        for (int r = slot; r < 3 * nc; r += QUAD) {
+            F(O_DGI + r) = 1.0f / F(O_AM + r * (r + 1) / 2 + r);
+            F(O_RES + r) = F(O_RHS + r);
+        }
+    }
+    SC_SYNC();
+    const int per_iter = 3 * ncmax, total = T.niter * per_iter;
+    for (int t = 0; t < total; t++) {
+        SC_STAGE {
+            SC_LANE;
+            const int nc = f2i(F(O_NC));
+            // apply the impulse change decided in the previous stage to the residuals this lane owns
+            int rp = -1;
+            if (t > 0) {
+                const int tl = (t - 1) % per_iter;
+                const int c = tl < ncmax ? tl : (tl - ncmax) >> 1;
+                if (c < nc) rp = tl < ncmax ? 3 * c : 3 * c + 1 + ((tl - ncmax) & 1);
+            }
+            const float dl = F(O_DEL + ((t + 1) & 1));
+            if (rp >= 0 && dl != 0.0f)
+                for (int i = slot; i < 3 * nc; i += QUAD) {
+                    const int hi = i > rp ? i : rp, lo = i > rp ? rp : i;
+                    F(O_RES + i) -= F(O_AM + hi * (hi + 1) / 2 + lo) * dl;
+                }
+            // the owner of the next row decides its impulse change
+            {
+                const int tl = t % per_iter;
+                const int c = tl < ncmax ? tl : (tl - ncmax) >> 1;
+                if (c < nc) {
+                    const int k = tl < ncmax ? 0 : 1 + ((tl - ncmax) & 1);
+                    const int r = 3 * c + k;
+                    if ((r & 3) == slot) {
+                        const float lam = F(O_LAM + r);
+                        float nl = lam + F(O_RES + r) * F(O_DGI + r);
+                        if (k == 0) nl = fmaxf(nl, 0.0f);
+                        else { const float lim = T.mu * F(O_LAM + 3 * c); nl = fminf(lim, fmaxf(-lim, nl)); }
+                        F(O_LAM + r) = nl;
+                        F(O_DEL + (t & 1)) = nl - lam;
+                    }
+                } else if (slot == 0) F(O_DEL + (t & 1)) = 0.0f;
+            }
+        }
+        SC_SYNC();
+    }
+    // ---- apply the impulses: one articulated response over the tree ------------------------------------------
+    for (int d = T.nlev - 1; d >= 0; d--) {
+        SC_STAGE {
+            SC_LANE;
+            const int b = T.level_start[d] + slot;
+            const int mask = f2i(F(O_TM)), nc = f2i(F(O_NC));
+            if (b < T.level_start[d + 1] && nc > 0 && ((mask >> b) & 1)) {
+                V3 pn = mk(0, 0, 0), pf = mk(0, 0, 0);
+                for (int k = 0; k < T.nchild[b]; k++) {
+                    const int c = T.child[b][k];
+                    if ((mask >> c) & 1) { pn = pn + ld3(S, O_PC + 6 * c); pf = pf + ld3(S, O_PC + 6 * c + 3); }
+                }
+                const M3 R = ldM(S, O_RW + 9 * b);
+                for (int j = 0; j < nc; j++) if (f2i(F(O_CB + j)) == b) {
+                    const V3 f = F(O_LAM + 3 * j) * cdir(R, 0) + F(O_LAM + 3 * j + 1) * cdir(R, 1) + F(O_LAM + 3 * j + 2) * cdir(R, 2);
+                    pn = pn - cross(ld3(S, O_CR + 3 * j), f);
+                    pf = pf - f;
+                }
+                if (b == 0) {
+                    float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
+#pragma unroll
+                    for (int i = 0; i < 21; i++) L[i] = F(O_I0L + i);
+                    solve6(L, x);
+#pragma unroll
+                    for (int i = 0; i < 6; i++) F(O_PC + i) = x[i];
+                    const V3 dw = mul(R, mk(x[0], x[1], x[2])), dv = mul(R, mk(x[3], x[4], x[5]));
+                    F(O_VB) += dw.x; F(O_VB + 1) += dw.y; F(O_VB + 2) += dw.z;
+                    F(O_VB + 3) += dv.x; F(O_VB + 4) += dv.y; F(O_VB + 5) += dv.z;
+                } else {
+                    const V3 u = neg(pn);
+                    st3(S, O_TP + 3 * b, u);
+                    const V3 Ku = mul(ldS(S, O_DI + 6 * b), u);
+                    pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
+                    pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
+                    const M3 Rj = ldRj(S, b);
+                    const V3 fp = mul(Rj, pf);
+                    st3(S, O_PC + 6 * b, mul(Rj, pn) + cross(tv3(T.jorg, b), fp));
+                    st3(S, O_PC + 6 * b + 3, fp);
+                }
+            }
+        }
+        SC_SYNC();
+    }
+    for (int d = 1; d < T.nlev; d++) {
+        SC_STAGE {
+            SC_LANE;
+            const int b = T.level_start[d] + slot;
+            const int mask = f2i(F(O_TM)), nc = f2i(F(O_NC));
+            if (b < T.level_start[d + 1] && nc > 0) {
+                const int p = T.parent[b];
+                const M3 Rj = ldRj(S, b);
+                const V3 alp = ld3(S, O_PC + 6 * p), ap = ld3(S, O_PC + 6 * p + 3);
+                const V3 aw = mulT(Rj, alp), al = mulT(Rj, ap + cross(alp, tv3(T.jorg, b)));
+                V3 u = mk(0, 0, 0);
+                if ((mask >> b) & 1) u = ld3(S, O_TP + 3 * b);
+                const V3 qdd = mul(ldS(S, O_DI + 6 * b), u - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
+                st3(S, O_PC + 6 * b, aw + qdd);
+                st3(S, O_PC + 6 * b + 3, al);
+                st3(S, O_W + 3 * b, ld3(S, O_W + 3 * b) + qdd);
+            }
+        }
+        SC_SYNC();
+    }
+}
+
+// ============================================================================================================
+// integration (semi-implicit Euler, exponential-map quaternion update, Bullet's velocity clamp)
+// ============================================================================================================
+SC_DEV void quat_step(float *S, int o, V3 w, float h, bool left) {
+    const float a = sqrtf(dot(w, w));
+    const float s = a < 1e-3f ? 0.5f * h - h * h * h * 0.020833333333f * a * a : sinf(0.5f * a * h) / a;
+    const float ex = w.x * s, ey = w.y * s, ez = w.z * s, ew = cosf(0.5f * a * h);
+    const float qx = F(o), qy = F(o + 1), qz = F(o + 2), qw = F(o + 3);
+    float x, y, z, ww;
+    if (left) {   // e (x) q
+        x = ew * qx + ex * qw + ey * qz - ez * qy; y = ew * qy - ex * qz + ey * qw + ez * qx;
+        z = ew * qz + ex * qy - ey * qx + ez * qw; ww = ew * qw - ex * qx - ey * qy - ez * qz;
+    } else {      // q (x) e
+        x = qw * ex + qx * ew + qy * ez - qz * ey; y = qw * ey - qx * ez + qy * ew + qz * ex;
+        z = qw * ez + qx * ey - qy * ex + qz * ew; ww = qw * ew - qx * ex - qy * ey - qz * ez;
+    }
+    const float n = rsq(x * x + y * y + z * z + ww * ww);
+    F(o) = x * n; F(o + 1) = y * n; F(o + 2) = z * n; F(o + 3) = ww * n;
+}
+
+template <class TT>
+SC_DEV void integrate(float *sm, const TT &T, int L0, int L1) {
+    SC_STAGE {
+        SC_LANE;
+        const float mv = T.maxvel, h = T.h;
+        for (int b = slot; b < T.nb; b += QUAD) {
+            if (b == 0) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) F(O_VB + i) = fminf(mv, fmaxf(-mv, F(O_VB + i)));
+                F(O_P0) += h * F(O_VB + 3); F(O_P0 + 1) += h * F(O_VB + 4); F(O_P0 + 2) += h * F(O_VB + 5);
+                quat_step(S, O_Q, ld3(S, O_VB), h, true);
+            } else {
+                V3 w = ld3(S, O_W + 3 * b);
+                w = mk(fminf(mv, fmaxf(-mv, w.x)), fminf(mv, fmaxf(-mv, w.y)), fminf(mv, fmaxf(-mv, w.z)));
+                st3(S, O_W + 3 * b, w);
+                quat_step(S, O_Q + 4 * b, w, h, false);
+            }
+        }
+    }
+    SC_SYNC();
+}
+
+// ============================================================================================================
+// state I/O in the reference's 132-float layout (humanoid_stable_pd.py:137-165)
+// ============================================================================================================
+SC_DEV int state_word(const Tables &T, int i) {
+    const int nj = T.nj;
+    if (i < 3) return O_P0 + i;
+    if (i < 7) return O_Q + (i - 3);
+    if (i < 7 + 4 * nj) { const int j = (i - 7) >> 2; return O_Q + 4 * T.jbody[j] + ((i - 7) & 3); }
+    i -= 7 + 4 * nj;
+    if (i < 3) return O_VB + 3 + i;
+    if (i < 6) return O_VB + (i - 3);
+    i -= 6;
+    return O_W + 3 * T.jbody[i / 3] + i % 3;
+}
+
+template <class TT>
+SC_DEV void load_state(float *sm, const TT &T, int L0, int L1, const float *rows, const int *parent_idx, int children, int tile0, int S_total) {
+    SC_STAGE {
+        SC_LANE;
+        int k = tile0 + (lane & 7);
+        if (k >= S_total) k = S_total - 1;   // padding lanes replay the last sample and never write
+        const float *src = rows + (size_t)(parent_idx ? parent_idx[k] : k / children) * SC_STATE_DIM;
+        for (int i = slot; i < SC_STATE_DIM; i += QUAD) F(state_word(T, i)) = src[i];
+    }
+    SC_SYNC();
+    SC_STAGE {
+        SC_LANE;
+        for (int b = slot; b < T.nb; b += QUAD) {
+            const int o = O_Q + 4 * b;
+            const float n = rsq(F(o) * F(o) + F(o + 1) * F(o + 1) + F(o + 2) * F(o + 2) + F(o + 3) * F(o + 3));
+            F(o) *= n; F(o + 1) *= n; F(o + 2) *= n; F(o + 3) *= n;
+        }
+    }
+    SC_SYNC();
+}
+
+// ============================================================================================================
+// cost features: link CoM positions / velocities -> whole-body CoM, end-effector positions
+// (humanoid_stable_pd.py:167-187, 218-222)
+// ============================================================================================================
+template <class TT>
+SC_DEV void features(float *sm, const TT &T, int L0, int L1) {
+    fk_sweep(sm, T, L0, L1, true);
+    SC_STAGE {
+        SC_LANE;
+        if (slot == 0) {
+            V3 cp = mk(0, 0, 0), cv = mk(0, 0, 0);
+            for (int i = 0; i < T.ncp; i++) {
+                const int b = T.cp_body[i];
+                const V3 off = tv3(T.cp_off, i);
+                const M3 R = ldM(S, O_RW + 9 * b);
+                const V3 p = ld3(S, O_PW + 3 * b) + mul(R, off);
+                const V3 v = mul(R, ld3(S, O_TW + 6 * b + 3) + cross(ld3(S, O_TW + 6 * b), off));
+                cp = cp + T.cp_mass[i] * p;
+                cv = cv + T.cp_mass[i] * v;
+                for (int e = 0; e < T.nee; e++) if (T.ee[e] == i) st3(S, O_FEAT + 6 + 3 * e, p);
+            }
+            st3(S, O_FEAT, T.inv_total_mass * cp);
+            st3(S, O_FEAT + 3, T.inv_total_mass * cv);
+        }
+    }
+    SC_SYNC();
+}
+
+SC_DEV float quat_angle(float ax, float ay, float az, float aw, float bx, float by, float bz, float bw) {
+    // rotation angle between two orientations, 2*acos(|<a,b>|) written through the relative quaternion's vector part
+    const float dx = bw * ax - bx * aw - by * az + bz * ay;
+    const float dy = bw * ay + bx * az - by * aw - bz * ax;
+    const float dz = bw * az - bx * ay + by * ax - bz * aw;
+    const float dw = bw * aw + bx * ax + by * ay + bz * az;
+    return 2.0f * atan2f(sqrtf(dx * dx + dy * dy + dz * dz), fabsf(dw));
+}
+
+// compute_total_cost (humanoid_tracking_env.py:78-176); kin = target state row, kf = its 18 features
+SC_DEV void cost_terms(const float *S, const Tables &T, const float *kin, const float *kf, float *out6) {
+    const int nj = T.nj;
+    float pose = 0;
+    for (int b = 1; b < T.nb; b++) {
+        const int j = T.jidx[b];
+        const float *q = kin + 7 + 4 * j, *w = kin + 13 + 4 * nj + 3 * j;
+        const float ang = quat_angle(F(O_Q + 4 * b), F(O_Q + 4 * b + 1), F(O_Q + 4 * b + 2), F(O_Q + 4 * b + 3), q[0], q[1], q[2], q[3]);
+        const V3 dw = ld3(S, O_W + 3 * b) - mk(w[0], w[1], w[2]);
+        pose += T.jw[b] * (ang * ang + 0.1f * dot(dw, dw));
+    }
+    pose /= (float)nj;
+    const float ang = quat_angle(F(O_Q), F(O_Q + 1), F(O_Q + 2), F(O_Q + 3), kin[3], kin[4], kin[5], kin[6]);
+    const float *kw = kin + 10 + 4 * nj;
+    const V3 dw = ld3(S, O_VB) - mk(kw[0], kw[1], kw[2]);
+    const float root = ang * ang + 0.1f * dot(dw, dw);
+    float ee = 0, bal = 0;
+    const V3 cs = ld3(S, O_FEAT), ck = mk(kf[0], kf[1], kf[2]);
+    for (int e = 0; e < T.nee; e++) {
+        const V3 ps = ld3(S, O_FEAT + 6 + 3 * e), pk = mk(kf[6 + 3 * e], kf[7 + 3 * e], kf[8 + 3 * e]);
+        const float dz = ps.z - pk.z;
+        ee += dz * dz;
+        const float bx = (cs.x - ps.x) - (ck.x - pk.x), by = (cs.y - ps.y) - (ck.y - pk.y);
+        bal += bx * bx + by * by;
+    }
+    ee /= (float)T.nee;
+    bal /= (float)T.nee * T.height;
+    const V3 dc = cs - ck, dcv = ld3(S, O_FEAT + 3) - mk(kf[3], kf[4], kf[5]);
+    const float com = dot(dc, dc) + 0.1f * dot(dcv, dcv);
+    out6[1] = pose; out6[2] = root; out6[3] = ee; out6[4] = bal; out6[5] = com;
+    out6[0] = T.cw[0] * pose + T.cw[1] * root + T.cw[2] * ee + T.cw[3] * bal + T.cw[4] * com;
+}
+
+// ============================================================================================================
+// one tile = 8 samples through a whole SamCon window
+// ============================================================================================================
+struct RolloutArgs {
+    const float *parents;      // [E,132]
+    const int *parent_idx;     // [S] or null
+    int children;
+    const float *actions;      // [S,4*nj]
+    const float *targets;      // [nseq,132]
+    const float *tfeat;        // [nseq,18]
+    const int *sample_seq;     // [S] or null
+    int S, nsteps;
+    float *out_state, *out_cost, *out_info;   // any may be null
+    float *out_feat;           // [S,18] or null (feature-only mode)
+    float *out_cost6;          // [S,6] total + 5 terms, or null (sc_cost)
+};
+
+template <class TT>
+SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0, int L0, int L1) {
+    load_state(sm, T, L0, L1, a.parents, a.parent_idx, a.children, tile0, a.S);
+    for (int step = 0; step < a.nsteps; step++) {
+        fk_sweep(sm, T, L0, L1, true);
+        SC_STAGE {
+            SC_LANE;
+            int k = tile0 + (lane & 7);
+            if (k >= a.S) k = a.S - 1;
+            const float *act = a.actions + (size_t)k * (4 * T.nj);
+            for (int b = 1 + slot; b < T.nb; b += QUAD) pd_term_body(S, T, b, act);
+        }
+        SC_SYNC();
+        aba<true>(sm, T, L0, L1);
+        for (int sub = 0; sub < T.nsub; sub++) {
+            if (sub) fk_sweep(sm, T, L0, L1, true);
+            collide(sm, T, L0, L1);
+            aba<false>(sm, T, L0, L1);
+            const int ncmax = tile_max_int(sm, O_NC);
+            if (ncmax > 0) {
+                fk_sweep(sm, T, L0, L1, false);
+                contact_solve(sm, T, L0, L1, ncmax);
+            }
+            integrate(sm, T, L0, L1);
+        }
+    }
+    features(sm, T, L0, L1);
+    SC_STAGE {
+        SC_LANE;
+        const int s = lane & 7, k = tile0 + s;
+        if (k < a.S) {
+            if (a.out_state) {
+                float *dst = a.out_state + (size_t)k * SC_STATE_DIM;
+                for (int i = slot; i < SC_STATE_DIM; i += QUAD) dst[i] = F(state_word(T, i));
+            }
+            if (a.out_feat) for (int i = slot; i < 18; i += QUAD) a.out_feat[(size_t)k * 18 + i] = F(O_FEAT + i);
+            if (slot == 0 && (a.out_cost || a.out_cost6)) {
+                const int q = a.sample_seq ? a.sample_seq[k] : 0;
+                float c[6];
+                cost_terms(S, T, a.targets + (size_t)q * SC_STATE_DIM, a.tfeat + (size_t)q * 18, c);
+                if (a.out_cost) a.out_cost[k] = c[0];
+                if (a.out_info) for (int i = 0; i < 5; i++) a.out_info[(size_t)k * 5 + i] = c[1 + i];
+                if (a.out_cost6) for (int i = 0; i < 6; i++) a.out_cost6[(size_t)k * 6 + i] = c[i];
+            }
+        }
+    }
+    SC_SYNC();
+}
+
+}  // namespace sc

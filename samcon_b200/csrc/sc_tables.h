@@ -1,0 +1,71 @@
+// sc_tables.h -- host: derive the kernel's lookup tables (sc::Tables) from the C-ABI model description.
+#pragma once
+#include <stdio.h>
+#include <string.h>
+#include "sc_core.cuh"
+
+namespace sc {
+
+inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) {
+#define SC_FAIL(...) do { snprintf(err, errlen, __VA_ARGS__); return SC_EINVAL; } while (0)
+    memset(T, 0, sizeof(*T));
+    if (!m) SC_FAIL("null model");
+    if (m->nb < 1 || m->nb > NB) SC_FAIL("nb=%d outside 1..%d", m->nb, NB);
+    if (m->nlev < 1 || m->nlev > MAXLEV) SC_FAIL("nlev=%d outside 1..%d", m->nlev, MAXLEV);
+    if (m->ncand < 0 || m->ncand > SC_MAX_CAND) SC_FAIL("ncand=%d > %d", m->ncand, SC_MAX_CAND);
+    if (m->ncp < 1 || m->ncp > SC_MAX_CPOINTS) SC_FAIL("ncp=%d outside 1..%d", m->ncp, SC_MAX_CPOINTS);
+    if (m->nee < 1 || m->nee > 4) SC_FAIL("nee=%d outside 1..4", m->nee);
+    if (m->max_contacts < 0 || m->max_contacts > MAXC) SC_FAIL("max_contacts=%d > %d", m->max_contacts, MAXC);
+    if (m->num_substeps < 1 || m->num_solver_iters < 0 || !(m->dt > 0)) SC_FAIL("bad engine settings");
+    if (7 + 4 * (m->nb - 1) + 6 + 3 * (m->nb - 1) != SC_STATE_DIM) SC_FAIL("state layout needs %d joints", (SC_STATE_DIM - 13) / 7);
+    T->nb = m->nb; T->nlev = m->nlev; T->ncand = m->ncand; T->ncp = m->ncp; T->nee = m->nee;
+    T->niter = m->num_solver_iters; T->nsub = m->num_substeps; T->maxc = m->max_contacts; T->nj = m->nb - 1;
+    for (int d = 0; d <= m->nlev; d++) T->level_start[d] = m->level_start[d];
+    if (T->level_start[0] != 0 || T->level_start[1] != 1 || T->level_start[m->nlev] != m->nb) SC_FAIL("bad level_start");
+    for (int d = 0; d < m->nlev; d++) {
+        int w = T->level_start[d + 1] - T->level_start[d];
+        if (w < 1 || w > QUAD) SC_FAIL("tree level %d has %d bodies (1..%d supported)", d, w, QUAD);
+    }
+    for (int b = 0; b < m->nb; b++) {
+        int p = m->parent[b];
+        if ((b == 0) != (p < 0) || p >= b) SC_FAIL("bodies must be listed parents-first (body %d)", b);
+        T->parent[b] = p;
+        T->depth[b] = b ? T->depth[p] + 1 : 0;
+        if (b < T->level_start[T->depth[b]] || b >= T->level_start[T->depth[b] + 1]) SC_FAIL("body %d not in its level", b);
+        T->anc_mask[b] = (1 << b) | (b ? T->anc_mask[p] : 0);
+        if (b) {
+            if (T->nchild[p] >= 4) SC_FAIL("body %d has more than 4 children", p);
+            T->child[p][T->nchild[p]++] = b;
+            int j = m->jidx[b];
+            if (j < 0 || j >= m->nb - 1) SC_FAIL("bad jidx for body %d", b);
+            T->jidx[b] = j; T->jbody[j] = b;
+        } else T->jidx[b] = -1;
+        for (int k = 0; k < 3; k++) T->jorg[3 * b + k] = m->jorg[3 * b + k];
+        for (int k = 0; k < 10; k++) { T->idyn[10 * b + k] = m->inertia_dyn[10 * b + k]; T->ipd[10 * b + k] = m->inertia_pd[10 * b + k]; }
+        T->kp[b] = m->kp[b]; T->kd[b] = m->kd[b]; T->maxf[b] = m->maxf[b]; T->jw[b] = m->joint_weights[b];
+    }
+    for (int c = 0; c < m->ncand; c++) {
+        if (m->cand_body[c] < 0 || m->cand_body[c] >= m->nb) SC_FAIL("bad cand_body");
+        T->cand_body[c] = m->cand_body[c];
+        for (int k = 0; k < 4; k++) T->cand[4 * c + k] = m->cand[4 * c + k];
+    }
+    double tm = 0;
+    for (int i = 0; i < m->ncp; i++) {
+        if (m->cp_body[i] < 0 || m->cp_body[i] >= m->nb) SC_FAIL("bad cp_body");
+        T->cp_body[i] = m->cp_body[i]; T->cp_mass[i] = m->cp_mass[i]; tm += m->cp_mass[i];
+        for (int k = 0; k < 3; k++) T->cp_off[3 * i + k] = m->cp_off[3 * i + k];
+    }
+    for (int e = 0; e < m->nee; e++) {
+        if (m->ee[e] < 0 || m->ee[e] >= m->ncp) SC_FAIL("bad end effector %d", m->ee[e]);
+        T->ee[e] = m->ee[e];
+    }
+    for (int k = 0; k < 5; k++) T->cw[k] = m->cost_weights[k];
+    T->height = m->height; T->dt = m->dt; T->h = m->dt / m->num_substeps;
+    for (int k = 0; k < 3; k++) T->g[k] = m->gravity[k];
+    T->mu = m->friction; T->erp = m->erp; T->cthresh = m->contact_threshold; T->maxvel = m->max_velocity;
+    T->inv_total_mass = (float)(1.0 / tm);
+    return SC_OK;
+#undef SC_FAIL
+}
+
+}  // namespace sc

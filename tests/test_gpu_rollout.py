@@ -1,0 +1,117 @@
+"""GPU parity: the CUDA rollout (through the C ABI) against the float64 oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: per-sample joint-state RMS error <= 1e-3 rad and cost within 1e-3 relative
+after one window; elite index sets equal whenever costs are separated by more than that tolerance.
+"""
+import numpy as np
+import pytest
+
+from helpers import joint_rms, near_action, rand_state, stand
+
+pytestmark = pytest.mark.gpu
+
+JOINT_TOL = 1e-3
+COST_RTOL = 1e-3
+
+
+def _run(pool, parents, actions, target, nsteps, children=None):
+    st, cost, info = pool.window(np.asarray(parents, np.float32), np.asarray(actions, np.float32),
+                                 np.asarray(target, np.float32), nsteps, children=children)
+    return st.cpu().numpy(), cost.cpu().numpy(), info.cpu().numpy()
+
+
+def test_cost_only(pool, oracle):
+    rng = np.random.default_rng(1)
+    parents = np.array([rand_state(rng, 1.0, 1.2) for _ in range(37)])
+    actions = np.array([near_action(p, rng, 0.1) for p in parents])
+    target = rand_state(rng, 0.5, 1.0)
+    st, cost, info = _run(pool, parents, actions, target, 0, 1)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 0)
+    np.testing.assert_allclose(st, ost, atol=2e-6)
+    np.testing.assert_allclose(cost, ocost, rtol=1e-4)
+    np.testing.assert_allclose(info, oinfo, rtol=1e-4, atol=1e-6)
+
+
+def test_airborne_window(pool, oracle):
+    rng = np.random.default_rng(2)
+    parents = np.array([rand_state(rng, 0.3, 3.0) for _ in range(24)])
+    actions = np.array([near_action(p, rng, 0.1) for p in parents])
+    target = rand_state(rng, 0.5, 1.0)
+    st, cost, info = _run(pool, parents, actions, target, 100, 1)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
+    assert joint_rms(st, ost).max() < JOINT_TOL
+    np.testing.assert_allclose(st[:, :3], ost[:, :3], atol=1e-4)
+    np.testing.assert_allclose(cost, ocost, rtol=COST_RTOL)
+
+
+def test_contact_window(pool, oracle):
+    """Standing / landing humanoids: foot boxes, partial support, speculative contacts."""
+    rng = np.random.default_rng(3)
+    parents = np.array([stand(rng, 0.05, 0.2, 0.98 + 0.004 * i) for i in range(16)])
+    actions = np.array([near_action(p, rng, 0.1) for p in parents])
+    target = stand(rng)
+    st, cost, info = _run(pool, parents, actions, target, 100, 1)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
+    assert joint_rms(st, ost).max() < JOINT_TOL
+    np.testing.assert_allclose(st[:, :3], ost[:, :3], atol=1e-4)
+    np.testing.assert_allclose(cost, ocost, rtol=COST_RTOL)
+    np.testing.assert_allclose(info, oinfo, rtol=5e-3, atol=1e-5)
+
+
+def test_walk_window_and_elites(pool, oracle):
+    """walk.yml-shaped window, reduced: E parents x 10 children, cfg noise, elite set vs oracle."""
+    from samcon_b200.sampling import get_batch_action
+    rng = np.random.default_rng(4)
+    E, children = 12, 10
+    parents = np.array([stand(rng, 0.03, 0.1, 0.985) for _ in range(E)])
+    target = stand(rng, 0.03, 0.1, 0.985)
+    from samcon_b200.config import Config
+    cfg = Config("walk")
+    actions = get_batch_action(target, E * children, cfg.values, "uniform", np.random.RandomState(1))
+    st, cost, info = _run(pool, parents, actions, target, 100)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
+    assert joint_rms(st, ost).max() < JOINT_TOL
+    np.testing.assert_allclose(cost, ocost, rtol=COST_RTOL)
+    idx, ec = pool.select(cost, E)
+    gi = idx.cpu().numpy()[0]
+    oi = oracle.topk(ocost, E)
+    # identical wherever the oracle's costs are separated by more than the tolerance
+    srt = np.sort(ocost)
+    sep = np.diff(srt)[:E] > 2 * COST_RTOL * srt[1:E + 1]
+    if sep.all():
+        assert list(gi) == list(oi)
+    else:
+        assert set(gi[: np.argmin(sep)]) == set(oi[: np.argmin(sep)])
+    assert list(gi) == list(np.lexsort((np.arange(len(cost)), cost))[:E])
+
+
+def test_step_and_cost_entry_points(pool, oracle):
+    rng = np.random.default_rng(5)
+    states = np.array([stand(rng, 0.05, 0.2, 1.0) for _ in range(9)])
+    actions = np.array([near_action(p, rng, 0.1) for p in states])
+    import torch
+    d = torch.tensor(states, dtype=torch.float32, device="cuda")
+    pool.step(d, actions, 20)
+    ost = np.array([oracle.step(s, a, 20) for s, a in zip(states, actions)])
+    assert joint_rms(d.cpu().numpy(), ost).max() < JOINT_TOL
+    kin = np.array([stand(rng) for _ in range(9)])
+    c = pool.cost(ost.astype(np.float32), kin.astype(np.float32)).cpu().numpy()
+    for i in range(9):
+        tot, terms = oracle.cost(ost[i], kin[i])
+        np.testing.assert_allclose(c[i, 0], tot, rtol=1e-4)
+        np.testing.assert_allclose(c[i, 1:], terms, rtol=1e-4, atol=1e-7)
+
+
+def test_ragged_sizes(pool, oracle):
+    """S not a multiple of the 8-sample tile, S=1, explicit parent_idx."""
+    rng = np.random.default_rng(6)
+    parents = np.array([stand(rng, 0.05, 0.2, 1.0) for _ in range(3)])
+    target = stand(rng)
+    for S in (1, 7, 13):
+        pidx = rng.integers(0, 3, size=S).astype(np.int32)
+        actions = np.array([near_action(parents[p], rng, 0.1) for p in pidx])
+        st, cost, info = pool.window(parents.astype(np.float32), actions.astype(np.float32), target.astype(np.float32), 10,
+                                     parent_idx=pidx)
+        ost, ocost, _ = oracle.window(parents[pidx], actions, target, 10)
+        assert joint_rms(st.cpu().numpy(), ost).max() < JOINT_TOL
+        np.testing.assert_allclose(cost.cpu().numpy(), ocost, rtol=COST_RTOL)
