@@ -1,0 +1,255 @@
+"""Reference-motion access: numpy restatement of the reference's ``AmassMotionData``
+(/root/reference/data_loaders/amass_motion_data.py:12-109) and of the PyBullet helpers it calls
+(/root/reference/utils/bullet_utils.py:9-45), plus a synthetic SMPL-shaped motion generator used where the
+reference reads ``data/motion/amass_bullet.pkl`` (not shipped, /root/reference/.gitignore:123).
+
+Motion dict format (process_amass/amass_to_bullet.py:118-121): ``{seq: {'fr': fps, 'pose': (T, 75) float64}}``
+with pose = root position (3), root quaternion xyzw (4), 17 joint quaternions xyzw (68).
+
+The three PyBullet calls are restated from bullet3's published quaternion code [BULLET-UPSTREAM, unverified]:
+``getQuaternionSlerp`` = shortest-arc slerp that returns the start orientation when the two are (anti)parallel;
+``getAxisAngleFromQuaternion`` = (xyz / sqrt(1 - w^2) or (1,0,0) if that is ~0, 2*acos(w)) with no
+shortest-path flip; ``multiplyTransforms`` with zero positions = quaternion product.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .model import STATE_DIM
+
+_EPS = np.finfo(np.float64).eps
+
+
+def quat_mul(a, b):
+    x, y, z, w = a
+    X, Y, Z, W = b
+    return np.array([w * X + x * W + y * Z - z * Y, w * Y - x * Z + y * W + z * X, w * Z + x * Y - y * X + z * W,
+                     w * W - x * X - y * Y - z * Z], dtype=np.float64)
+
+
+def quat_slerp(q0, q1, t):
+    q0 = np.asarray(q0, dtype=np.float64)
+    q1 = np.asarray(q1, dtype=np.float64)
+    mag = math.sqrt(np.dot(q0, q0) * np.dot(q1, q1))
+    prod = float(np.dot(q0, q1)) / mag
+    ap = abs(prod)
+    if ap < 1.0 - _EPS:
+        theta = math.acos(ap)
+        d = math.sin(theta)
+        sign = -1.0 if prod < 0 else 1.0
+        s0 = math.sin((1.0 - t) * theta) / d
+        s1 = math.sin(sign * t * theta) / d
+        return q0 * s0 + q1 * s1
+    return q0.copy()
+
+
+def axis_angle_from_quat(q):
+    x, y, z, w = (float(v) for v in q)
+    s2 = 1.0 - w * w
+    if s2 < 10.0 * _EPS:
+        axis = np.array([1.0, 0.0, 0.0])
+    else:
+        axis = np.array([x, y, z]) / math.sqrt(s2)
+    return axis, 2.0 * math.acos(max(-1.0, min(1.0, w)))
+
+
+def compute_lin_vel(p0, p1, dt):          # bullet_utils.py:9-15
+    return (np.asarray(p1, dtype=np.float64) - np.asarray(p0, dtype=np.float64)) / dt
+
+
+def compute_ang_vel(q0, q1, dt):          # bullet_utils.py:17-30, world frame (base)
+    q0c = np.array([-q0[0], -q0[1], -q0[2], q0[3]])
+    axis, ang = axis_angle_from_quat(quat_mul(q1, q0c))
+    return axis * ang / dt
+
+
+def compute_ang_vel_rel(q0, q1, dt):      # bullet_utils.py:32-45, local frame (joints)
+    q0c = np.array([-q0[0], -q0[1], -q0[2], q0[3]])
+    axis, ang = axis_angle_from_quat(quat_mul(q0c, q1))
+    return axis * ang / dt
+
+
+class AmassMotionData:
+    """Same constructor and methods as the reference class; ``path`` may also be an in-memory motion dict."""
+
+    def __init__(self, path, seq):
+        if isinstance(path, dict):
+            data = path[seq]
+        else:
+            import joblib
+            data = joblib.load(path)[seq]
+        self._duration = 1.0 / data["fr"]
+        self._motion = np.asarray(data["pose"], dtype=np.float64)
+
+    def numFrames(self):
+        return self._motion.shape[0]
+
+    def keyFrameDuration(self):
+        return self._duration
+
+    def getCycleTime(self):
+        return self.keyFrameDuration() * (self.numFrames() - 1)
+
+    def calcCycleCount(self, curTime, cycleTime):
+        return math.floor(curTime / cycleTime)
+
+    def computeCycleOffset(self):
+        return self._motion[-1][:3] - self._motion[0][:3]
+
+    def getSpecTimeState(self, t):
+        curTime = t
+        keyFrameDuration = self.keyFrameDuration()
+        cycleTime = self.getCycleTime()
+        cycleCount = self.calcCycleCount(curTime, cycleTime)
+        frameTime = curTime - cycleCount * cycleTime
+        if frameTime < 0:
+            frameTime += cycleTime
+        frame = int(frameTime / keyFrameDuration)
+        frameNext = frame + 1
+        if frameNext >= self.numFrames():
+            frameNext = frame
+        frameFraction = (frameTime - frame * keyFrameDuration) / keyFrameDuration
+        state = self.interpolator(frameFraction, self._motion[frame], self._motion[frameNext])
+        state[0:3] = state[0:3] + cycleCount * self.computeCycleOffset()
+        return state
+
+    def interpolator(self, frameFraction, frameData, frameDataNext):
+        dt = self.keyFrameDuration()
+        basePos = frameData[0:3] + frameFraction * (frameDataNext[0:3] - frameData[0:3])
+        baseLinVel = compute_lin_vel(frameData[0:3], frameDataNext[0:3], dt)
+        baseOrn = quat_slerp(frameData[3:7], frameDataNext[3:7], frameFraction)
+        baseAngVel = compute_ang_vel(frameData[3:7], frameDataNext[3:7], dt)
+        j0 = frameData[7:].reshape(-1, 4)
+        j1 = frameDataNext[7:].reshape(-1, 4)
+        rots = [quat_slerp(a, b, frameFraction) for a, b in zip(j0, j1)]
+        vels = [compute_ang_vel_rel(a, b, dt) for a, b in zip(j0, j1)]
+        return np.concatenate((basePos, baseOrn, np.concatenate(rots), baseLinVel, baseAngVel, np.concatenate(vels)))
+
+    def all_window_states(self, nIter, sample_timestep):
+        """Targets of windows 0..nIter as one (nIter+1, 132) array (what SamCon.sample asks for one by one)."""
+        return np.stack([self.getSpecTimeState(t * sample_timestep) for t in range(nIter + 1)])
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic SMPL-shaped motions: in the loader's dict format, deterministic
+# ----------------------------------------------------------------------------------------------------------
+JOINTS = ["lhip", "lknee", "lankle", "rhip", "rknee", "rankle", "lowerback", "upperback", "chest", "lowerneck",
+          "upperneck", "lclavicle", "lshoulder", "lelbow", "rclavicle", "rshoulder", "relbow"]
+
+
+def _qx(a):
+    return np.array([math.sin(0.5 * a), 0.0, 0.0, math.cos(0.5 * a)])
+
+
+def _qaxis(axis, a):
+    axis = np.asarray(axis, dtype=np.float64)
+    return np.concatenate([math.sin(0.5 * a) * axis / np.linalg.norm(axis), [math.cos(0.5 * a)]])
+
+
+def _lowest_point(links, pose):
+    """Height of the lowest collision point of the character for one (75,) pose with root z = 0."""
+    from .urdf import BOX, CAPSULE, J_SPHERICAL
+    from scipy.spatial.transform import Rotation as sRot
+    R = [None] * len(links)
+    p = [None] * len(links)
+    R[0] = sRot.from_quat(pose[3:7]).as_matrix()
+    p[0] = np.array([0.0, 0.0, 0.0])
+    j = 0
+    zmin = np.inf
+    for i, l in enumerate(links):
+        if i:
+            Rj = np.eye(3)
+            if l.jtype == J_SPHERICAL:
+                Rj = sRot.from_quat(pose[7 + 4 * j:11 + 4 * j]).as_matrix()
+                j += 1
+            R[i] = R[l.parent] @ Rj
+            p[i] = p[l.parent] + R[l.parent] @ l.jorg
+        for s in l.shapes:
+            c = p[i] + R[i] @ s.pos
+            Rs = R[i] @ s.rot
+            if s.kind == BOX:
+                h = 0.5 * s.dims
+                z = c[2] - np.abs(Rs[2]) @ h
+            elif s.kind == CAPSULE:
+                z = c[2] - abs(Rs[2, 2]) * 0.5 * s.dims[1] - s.dims[0]
+            else:
+                z = c[2] - s.dims[0]
+            zmin = min(zmin, z)
+    return zmin
+
+
+def make_synthetic_motion(kind="walk", T=91, fr=30, seed=0, links=None, name=None):
+    """-> {name: {'fr': fr, 'pose': (T,75)}}.
+
+    walk: upright SMPL-like gait, root travels along the facing direction (-Y world: the character's links hang
+    along local -Y and toes point to local +Z, so the AMASS "upright" root rotation is +90 deg about X), hips
+    +-0.45 rad at 1 Hz in antiphase, knees 0..0.8 rad, ankles compensating, shoulders swinging +-0.3 rad, small
+    seeded per-sequence variation.  cartwheel: whole-body rotation of 2*pi about the forward axis over 1.5 s with
+    arms raised so that hands reach the ground, legs spread.
+    Root height is set frame by frame so that the lowest collision point touches the ground.
+    """
+    if links is None:
+        from .urdf import load_links
+        links = load_links(None)
+    rng = np.random.default_rng(seed)
+    amp = 1.0 + 0.1 * rng.standard_normal(6)
+    phase0 = rng.uniform(0, 2 * np.pi)
+    name = name or f"synthetic_{kind}_{seed}"
+    up = _qx(0.5 * np.pi)
+    pose = np.zeros((T, 75))
+    for f in range(T):
+        t = f / fr
+        q = {n: np.array([0.0, 0.0, 0.0, 1.0]) for n in JOINTS}
+        if kind == "walk":
+            ph = 2 * np.pi * 1.0 * t + phase0
+            hip = 0.45 * amp[0]
+            # flexion (leg forward, local +Z) is a negative rotation about local X
+            q["lhip"] = _qx(-hip * math.sin(ph))
+            q["rhip"] = _qx(hip * math.sin(ph))
+            q["lknee"] = _qx(0.8 * amp[1] * max(0.0, math.sin(ph - 0.5 * np.pi)) ** 2 + 0.05)
+            q["rknee"] = _qx(0.8 * amp[1] * max(0.0, math.sin(ph + 0.5 * np.pi)) ** 2 + 0.05)
+            q["lankle"] = _qx(0.15 * amp[2] * math.sin(ph + 0.3))
+            q["rankle"] = _qx(-0.15 * amp[2] * math.sin(ph + 0.3))
+            q["lshoulder"] = quat_mul(_qaxis([0, 0, 1], -1.2), _qx(0.3 * amp[3] * math.sin(ph)))
+            q["rshoulder"] = quat_mul(_qaxis([0, 0, 1], 1.2), _qx(-0.3 * amp[3] * math.sin(ph)))
+            q["lelbow"] = _qaxis([0, 1, 0], -0.3)
+            q["relbow"] = _qaxis([0, 1, 0], 0.3)
+            q["upperback"] = _qaxis([0, 1, 0], 0.08 * amp[4] * math.sin(ph))
+            root_q = quat_mul(_qaxis([0, 0, 1], 0.03 * amp[5] * math.sin(ph)), up)
+            root_xy = np.array([0.0, -1.0 * t])
+        elif kind == "cartwheel":
+            dur = 1.5
+            s = min(1.0, max(0.0, (t - 0.5) / dur))
+            s = 0.5 - 0.5 * math.cos(np.pi * s)                       # ease in/out
+            # spin about the forward axis (world -Y) after standing for 0.5 s
+            root_q = quat_mul(_qaxis([0, -1, 0], 2 * np.pi * s), up)
+            spread = 0.5 * math.sin(np.pi * s) * amp[0]
+            q["lhip"] = _qaxis([0, 0, 1], spread)
+            q["rhip"] = _qaxis([0, 0, 1], -spread)
+            raise_ = 1.4 * math.sin(np.pi * s) * amp[1]
+            q["lshoulder"] = _qaxis([0, 0, 1], -1.2 + raise_ + 1.2 * math.sin(np.pi * s))
+            q["rshoulder"] = _qaxis([0, 0, 1], 1.2 - raise_ - 1.2 * math.sin(np.pi * s))
+            root_xy = np.array([-1.2 * s, 0.0])
+        else:
+            raise ValueError(kind)
+        pose[f, 3:7] = root_q / np.linalg.norm(root_q)
+        for k, n in enumerate(JOINTS):
+            pose[f, 7 + 4 * k:11 + 4 * k] = q[n]
+        pose[f, 0:2] = root_xy
+        pose[f, 2] = -_lowest_point(links, pose[f]) + 0.001
+    # keep quaternion signs continuous so finite-difference velocities stay small (see module docstring)
+    for f in range(1, T):
+        for k in range(18):
+            a, b = pose[f - 1, 3 + 4 * k:7 + 4 * k], pose[f, 3 + 4 * k:7 + 4 * k]
+            if np.dot(a, b) < 0:
+                pose[f, 3 + 4 * k:7 + 4 * k] = -b
+    return {name: {"fr": fr, "pose": pose}}
+
+
+def check_state(state):
+    s = np.asarray(state)
+    if s.shape[-1] != STATE_DIM:
+        raise ValueError(f"expected {STATE_DIM}-float states")
+    return s

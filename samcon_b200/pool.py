@@ -178,11 +178,17 @@ class GpuSamplePool:
         """("sim", ...) for all jobs at once -- samcon.py:28-41.  Host in, host out (float64 like the reference)."""
         if self._elites is None:
             raise RuntimeError("init() must be called before sim()")
-        st, cost, info = self.window(self._elites, np.asarray(actions, dtype=np.float32),
-                                     np.asarray(target_state, dtype=np.float32), nsteps)
+        if not isinstance(actions, torch.Tensor):
+            actions = np.asarray(actions, dtype=np.float32)
+        st, cost, info = self.window(self._elites, actions, np.asarray(target_state, dtype=np.float32), nsteps)
         self._last = (st, cost, info)
         return (st.cpu().numpy().astype(np.float64), cost.cpu().numpy().astype(np.float64),
                 info.cpu().numpy().astype(np.float64))
+
+    def select_last(self, nSave):
+        """Trajectory.select('greedy') on the device for the window just simulated -> host int64 indices."""
+        idx, _ = self.select(self._last[1], nSave)
+        return idx[0].cpu().numpy().astype(np.int64)
 
     def keep(self, elite_inds):
         """Make the samples picked by Trajectory.select the parents of the next window (state stays in HBM)."""

@@ -1,0 +1,88 @@
+"""The rollout kernel's arithmetic (samcon_b200/csrc/sc_core.cuh compiled for the host as a lane loop, float32)
+against the float64 oracle, so kernel logic regressions are caught on a box without a GPU.  The emulation is a
+test aid only -- the package never loads it; the GPU parity proper is tests/test_gpu_rollout.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import joint_rms, near_action, rand_state, stand
+from samcon_b200.abi import make_model
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(HERE, "emu", "emu.cpp")
+    lib = os.path.join(HERE, "emu", "libsc_emu.so")
+    deps = [src] + [os.path.join(HERE, "..", "samcon_b200", "csrc", f) for f in ("sc_core.cuh", "sc_tables.h")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-o", lib, src])
+    return C.CDLL(lib)
+
+
+def _window(emu, character, parents, actions, targets, nsteps, children=1, parent_idx=None, sample_seq=None):
+    m, keep = make_model(character)
+    parents = np.ascontiguousarray(parents, np.float32)
+    actions = np.ascontiguousarray(actions, np.float32)
+    targets = np.ascontiguousarray(targets, np.float32).reshape(-1, 132)
+    S, E = len(actions), len(parents)
+    st = np.zeros((S, 132), np.float32)
+    cost = np.zeros(S, np.float32)
+    info = np.zeros((S, 5), np.float32)
+    err = C.create_string_buffer(256)
+
+    def p(a):
+        return a.ctypes.data_as(C.c_void_p) if a is not None else None
+    pi = np.ascontiguousarray(parent_idx, np.int32) if parent_idx is not None else None
+    sq = np.ascontiguousarray(sample_seq, np.int32) if sample_seq is not None else None
+    rc = emu.emu_window(C.byref(m), p(parents), E, p(pi), children, p(actions), p(targets), len(targets), p(sq), S, nsteps,
+                        p(st), p(cost), p(info), err, 256)
+    assert rc == 0, err.value
+    return st, cost, info
+
+
+def test_airborne(emu, character, oracle):
+    rng = np.random.default_rng(2)
+    parents = np.array([rand_state(rng, 0.3, 3.0) for _ in range(10)])
+    actions = np.array([near_action(p, rng, 0.1) for p in parents])
+    target = rand_state(rng, 0.5, 1.0)
+    st, cost, info = _window(emu, character, parents, actions, target, 50)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 50)
+    assert joint_rms(st, ost).max() < 1e-4
+    np.testing.assert_allclose(cost, ocost, rtol=1e-3)
+
+
+def test_contact_window(emu, character, oracle):
+    rng = np.random.default_rng(3)
+    parents = np.array([stand(rng, 0.05, 0.2, 0.98 + 0.005 * i) for i in range(9)])
+    actions = np.array([near_action(p, rng, 0.1) for p in parents])
+    target = stand(rng)
+    st, cost, info = _window(emu, character, parents, actions, target, 100)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
+    assert joint_rms(st, ost).max() < 1e-3
+    np.testing.assert_allclose(st[:, :3], ost[:, :3], atol=1e-4)
+    np.testing.assert_allclose(cost, ocost, rtol=1e-3)
+    np.testing.assert_allclose(info, oinfo, rtol=5e-3, atol=1e-5)
+
+
+def test_parent_mapping_and_sequences(emu, character, oracle):
+    """children = S/E mapping (sample k <- elite k // children), explicit parent_idx, per-sample target sequences."""
+    rng = np.random.default_rng(4)
+    parents = np.array([stand(rng, 0.05, 0.2, 1.0) for _ in range(3)])
+    targets = np.array([stand(rng) for _ in range(2)])
+    actions = np.array([near_action(parents[k // 2], rng, 0.1) for k in range(6)])
+    st, cost, _ = _window(emu, character, parents, actions, targets[0], 10, children=2)
+    ost, ocost, _ = oracle.window(parents, actions, targets[0], 10)
+    assert joint_rms(st, ost).max() < 1e-4
+    pidx = np.array([2, 0, 1, 1, 0, 2, 2])
+    seq = np.array([0, 1, 1, 0, 1, 0, 1])
+    actions = np.array([near_action(parents[p], rng, 0.1) for p in pidx])
+    st, cost, _ = _window(emu, character, parents, actions, targets, 10, parent_idx=pidx, sample_seq=seq)
+    for k in range(7):
+        os_, oc, _ = oracle.window(parents[pidx[k]][None], actions[k][None], targets[seq[k]], 10)
+        assert joint_rms(st[k][None], os_).max() < 1e-4
+        np.testing.assert_allclose(cost[k], oc[0], rtol=1e-3)

@@ -1,0 +1,116 @@
+"""Host side of the path: motion loader restatement, Trajectory, the SamCon loop (on an oracle-backed pool)."""
+import numpy as np
+import pytest
+
+from oracle_pool import OraclePool
+from samcon_b200.config import Config
+from samcon_b200.motion import AmassMotionData, make_synthetic_motion, quat_slerp
+from samcon_b200.samcon import SamCon, UniqueId
+from samcon_b200.trajectory import Trajectory
+
+
+@pytest.fixture(scope="module")
+def motion():
+    return make_synthetic_motion("walk", T=31, seed=0)
+
+
+def test_config_keys():
+    cfg = Config("walk")
+    assert (cfg.fps_sim, cfg.fps_act, cfg.seed, cfg.nIter, cfg.nSample, cfg.nSave) == (1000, 10, 1, 30, 2000, 200)
+    assert cfg.values.shape == (51,) and cfg.kps.shape == (17,) and cfg.char_info["max_forces"][0] == 300.0
+    assert cfg.end_effectors == [14, 18, 2, 5] and cfg.cost_weights == [0, 5, 20, 100, 50]
+    c2 = Config("cartwheel")
+    assert c2.nIter == 50 and c2.cost_weights == [0, 10, 60, 30, 10]
+    with pytest.raises(FileNotFoundError):
+        Config("nope")
+
+
+def test_synthetic_motion_shape_and_ground(motion, character):
+    (name, d), = motion.items()
+    assert d["fr"] == 30 and d["pose"].shape == (31, 75)
+    q = d["pose"][:, 3:].reshape(31, 18, 4)
+    assert np.allclose(np.linalg.norm(q, axis=-1), 1.0)
+    assert 0.9 < d["pose"][0, 2] < 1.05                           # SMPL-like root height
+    assert (np.diff(d["pose"][:, 1]) < 0).all()                    # walks along the facing direction (-Y)
+
+
+def test_motion_loader_interpolation(motion):
+    (name, d), = motion.items()
+    m = AmassMotionData(motion, name)
+    assert m.numFrames() == 31 and np.isclose(m.getCycleTime(), 1.0)
+    s0 = m.getSpecTimeState(0.0)
+    assert s0.shape == (132,) and np.allclose(s0[:75], d["pose"][0])
+    # root linear velocity = finite difference of key frames (bullet_utils.py:9-15)
+    assert np.allclose(s0[75:78], (d["pose"][1, :3] - d["pose"][0, :3]) * 30)
+    # halfway between frames: slerp midpoint and lerp of position
+    sh = m.getSpecTimeState(0.5 / 30)
+    assert np.allclose(sh[:3], 0.5 * (d["pose"][0, :3] + d["pose"][1, :3]))
+    assert np.allclose(sh[3:7], quat_slerp(d["pose"][0, 3:7], d["pose"][1, 3:7], 0.5))
+    # wrap-around adds the cycle offset (amass_motion_data.py:72-76)
+    s_wrap = m.getSpecTimeState(1.0 + 0.1)
+    s_in = m.getSpecTimeState(0.1)
+    assert np.allclose(s_wrap[:3] - s_in[:3], d["pose"][-1, :3] - d["pose"][0, :3])
+    assert np.allclose(s_wrap[3:], s_in[3:])
+    # joint angular velocity reproduces the frame-to-frame rotation
+    from scipy.spatial.transform import Rotation as R
+    j = 0
+    w = s0[81:84]
+    r = R.from_quat(d["pose"][0, 7:11]).inv() * R.from_quat(d["pose"][1, 7:11])
+    assert np.allclose(w / 30, r.as_rotvec(), atol=1e-9)
+
+
+def test_unique_id_and_trajectory_paths():
+    u = UniqueId()
+    assert list(u.get(1)) == [0] and list(u.get(3)) == [1, 2, 3]
+    nIter, S, E = 3, 6, 2
+    tr = Trajectory(nIter, S, E)
+    for _ in range(S):
+        tr.push(0, [-1, 0, np.zeros(132), None, None, 0.0, None])
+    tr.select(0)
+    rng = np.random.default_rng(0)
+    uid = 1
+    for t in range(1, nIter + 1):
+        prev = tr.get_curr_uid_elite(t - 1)
+        cost = rng.random(S)
+        for k in range(S):
+            tr.push(t, [prev[k // 3], uid, np.full(132, t), np.full(132, uid), np.full(68, uid), cost[k], list(cost[k] * np.ones(5))])
+            uid += 1
+        tr.select(t, "greedy")
+        assert list(tr.get_elite_inds(t)) == list(np.argsort(cost)[:E])
+    out, info = tr.build_results("seq")
+    assert set(out["seq"]) == {"path_0", "path_1"}
+    p0 = out["seq"]["path_0"]
+    assert p0["simulated_state"].shape == (3, 132) and p0["action"].shape == (3, 68) and p0["cost"].shape == (3, 1)
+    assert p0["total_cost"] <= out["seq"]["path_1"]["total_cost"]
+    # the path is a chain: each elite's parent is the previous step's uid
+    uids = p0["simulated_state"][:, 0].astype(int)
+    for a, b in zip(uids[:-1], uids[1:]):
+        assert tr._parent_of[b] == a
+    assert info["total_cost"].shape == (3, 6) and info["elite_inds"].shape == (3, 2) and info["best_path_my_sys"].shape == (3,)
+    with pytest.raises(NotImplementedError):
+        tr.select(1, "diversity")
+
+
+def test_samcon_loop_on_oracle_pool(oracle, motion):
+    (name, _), = motion.items()
+    cfg = Config("walk")
+    cfg.motion_seq = name
+    loader = AmassMotionData(motion, name)
+    sc = SamCon(cfg, loader, num_processes=8, nIter=2, nSample=20, nSave=4, pool=OraclePool(oracle))
+    out, info = sc.sample(save=False)
+    assert len(out[name]) == 4
+    p0 = out[name]["path_0"]
+    assert p0["simulated_state"].shape == (2, 132) and np.isfinite(p0["total_cost"])
+    assert np.allclose(p0["t0_state"], loader.getSpecTimeState(0.0))
+    assert np.allclose(p0["target_state"][1], loader.getSpecTimeState(0.2))
+    assert info["total_cost"].shape == (2, 20)
+    # elites are the cheapest samples, ascending
+    for t in range(2):
+        e = info["elite_inds"][t]
+        assert list(e) == list(np.lexsort((np.arange(20), info["total_cost"][t]))[:4])
+    # same seed -> same search (np.random.seed(cfg.seed) semantics)
+    sc2 = SamCon(cfg, loader, 1, 2, 20, 4, pool=OraclePool(oracle))
+    out2, _ = sc2.sample(save=False)
+    assert np.array_equal(out2[name]["path_0"]["action"], p0["action"])
+    with pytest.raises(Exception, match="multiples of nSave"):
+        SamCon(cfg, loader, 1, 2, 21, 4, pool=OraclePool(oracle))

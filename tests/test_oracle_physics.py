@@ -1,0 +1,130 @@
+"""Self-consistency of the CPU oracle (the reference ships no tests and no goldens for the physics -- SURVEY.md §4,
+§8c -- so the oracle is pinned by the identities any correct restatement must satisfy)."""
+import numpy as np
+import pytest
+
+from helpers import near_action, rand_state, stand
+
+
+def _energy(o, ch, s):
+    M = o.mass_matrix(s, 0)
+    v = o.gen_vel(s)
+    pos, _, _, _ = o.link_coms(s)
+    m = np.array([l.mass for l in ch.links])
+    return 0.5 * v @ M @ v + 9.8 * (m * pos[:, 2]).sum()
+
+
+@pytest.mark.parametrize("iset", [0, 1])
+def test_mass_matrix_spd_and_matches_rnea(oracle, iset):
+    rng = np.random.default_rng(0)
+    s = rand_state(rng)
+    M = oracle.mass_matrix(s, iset)
+    assert np.abs(M - M.T).max() < 1e-12 and np.linalg.eigvalsh(M).min() > 0
+    assert abs(np.trace(M[3:6, 3:6]) / 3 - 53.5) < 1e-9           # total mass in the base linear block
+    c0 = oracle.bias(s, iset, gravity=False)
+    for i in range(0, 57, 4):                                     # M e_i = RNEA(q, v, e_i) - RNEA(q, v, 0)
+        e = np.zeros(57)
+        e[i] = 1
+        assert np.abs(oracle.bias(s, iset, False, e) - c0 - M[:, i]).max() < 1e-10
+
+
+def test_free_flight_conservation(oracle, character):
+    """Zero torques, far above the ground: energy drift and momentum error are first-order in dt."""
+    rng = np.random.default_rng(5)
+    s = rand_state(rng, 1.0, 5.0)
+    e0 = _energy(oracle, character, s)
+    _, _, c0, v0 = oracle.link_coms(s)
+    s2 = oracle.step_torque(s, np.zeros(57), 400)                 # 0.2 s of 0.5 ms sub-steps
+    e1 = _energy(oracle, character, s2)
+    _, _, c1, v1 = oracle.link_coms(s2)
+    assert abs(e1 - e0) / abs(e0) < 5e-4
+    g = np.array([0, 0, -9.8])
+    assert np.abs(v1 - (v0 + 0.2 * g)).max() < 3e-3               # horizontal momentum kept, vertical follows g
+    assert np.abs(c1 - (c0 + 0.2 * v0 + 0.5 * g * 0.04)).max() < 3e-3
+
+
+def test_momentum_error_is_first_order_in_dt(walk_cfg):
+    from samcon_b200.model import Character, SimParams
+    from oracle.oracle import Oracle
+    errs = []
+    for dt, n in ((1e-3, 400), (5e-4, 800)):
+        o = Oracle(Character.from_config(walk_cfg, SimParams(dt=dt)))
+        s = rand_state(np.random.default_rng(5), 1.0, 5.0)
+        _, _, _, v0 = o.link_coms(s)
+        _, _, _, v1 = o.link_coms(o.step_torque(s, np.zeros(57), n))
+        errs.append(np.abs(v1 - v0 - 0.2 * np.array([0, 0, -9.8]))[:2].max())
+    assert 1.7 < errs[0] / errs[1] < 2.3
+
+
+def test_stable_pd_reduces_to_pd_and_clamps(oracle, character):
+    rng = np.random.default_rng(1)
+    s = rand_state(rng, 0.0, 3.0)
+    s[75:] = 0
+    a = near_action(s, rng, 0.02)
+    tau = oracle.pd_torque(s, a)
+    assert np.all(tau[:6] == 0)
+    mf = np.repeat(character.max_forces, 3)
+    assert np.all(np.abs(tau[6:]) <= mf + 1e-12)
+    big = near_action(s, rng, 2.5)
+    assert np.isclose(np.abs(oracle.pd_torque(s, big)[6:]) / mf, 1.0).any()      # saturates somewhere
+
+
+def test_stable_pd_is_stable_at_reference_gains(oracle):
+    """kp 500 / kd 50 at dt = 1 ms would blow up with explicit PD on the light links; stable PD must settle."""
+    rng = np.random.default_rng(2)
+    s = rand_state(rng, 0.0, 5.0, amp=0.2)
+    s[75:] = 0
+    a = near_action(s, rng, 0.1)
+    for _ in range(3):
+        s = oracle.step(s, a, 100)
+    assert np.abs(s[81:]).max() < 1.0
+    d = np.abs((s[7:75].reshape(17, 4) * a.reshape(17, 4)).sum(-1))
+    assert (2 * np.arccos(np.clip(d, 0, 1))).max() < 0.1
+
+
+def test_standing_contacts(oracle):
+    rng = np.random.default_rng(3)
+    s = stand(rng, 0.0, 0.0, 1.0)
+    s[0:2] = 0
+    a = s[7:75].copy()
+    s = oracle.step(s, a, 200)
+    c = oracle.contacts(s)
+    assert len(c) == 8 and set(c[:, 0].astype(int)) == {3, 6}      # four corners of each foot box
+    assert np.abs(c[:, 4]).max() < 1e-3                            # resting on the plane, no sinking
+    assert 0.97 < s[2] < 1.0
+
+
+def test_contact_cap_keeps_deepest(oracle, character):
+    rng = np.random.default_rng(4)
+    s = stand(rng, 0.0, 0.0, 0.95)                                  # feet 4 cm into the ground
+    c = oracle.contacts(s)
+    assert len(c) == character.sim.max_contacts
+    assert (c[:, 4] < 0).all()
+
+
+def test_cost_terms_against_numpy(oracle, character, walk_cfg):
+    """/root/reference/envs/humanoid_tracking_env.py:78-176 written out with numpy on the oracle's link CoMs."""
+    rng = np.random.default_rng(6)
+    a, b = rand_state(rng, 1.0, 1.0), rand_state(rng, 1.0, 1.0)
+    tot, (pose, root, ee, bal, com) = oracle.cost(a, b)
+    pa, va, ca, cva = oracle.link_coms(a)
+    pb, vb, cb, cvb = oracle.link_coms(b)
+
+    def ang(q0, q1):
+        return 2 * np.arccos(min(1.0, abs(np.dot(q0, q1))))
+    jw = np.array(walk_cfg.joint_weights)
+    p = sum(jw[j] * (ang(a[7 + 4 * j:11 + 4 * j], b[7 + 4 * j:11 + 4 * j]) ** 2
+                     + 0.1 * np.sum((a[81 + 3 * j:84 + 3 * j] - b[81 + 3 * j:84 + 3 * j]) ** 2)) for j in range(17)) / 17
+    r = ang(a[3:7], b[3:7]) ** 2 + 0.1 * np.sum((a[78:81] - b[78:81]) ** 2)
+    ees = [e + 1 for e in walk_cfg.end_effectors]
+    e_ = np.mean([(pa[i, 2] - pb[i, 2]) ** 2 for i in ees])
+    bl = sum(np.sum((((ca - pa[i]) - (cb - pb[i]))[:2]) ** 2) for i in ees) / (4 * walk_cfg.height)
+    cm = np.sum((ca - cb) ** 2) + 0.1 * np.sum((cva - cvb) ** 2)
+    assert np.allclose([pose, root, ee, bal, com], [p, r, e_, bl, cm], rtol=1e-10)
+    assert np.isclose(tot, np.dot(walk_cfg.cost_weights, [p, r, e_, bl, cm]))
+    assert oracle.cost(a, a)[0] < 1e-12
+
+
+def test_topk_ties_by_index(oracle):
+    c = np.array([3.0, 1.0, 2.0, 1.0, 5.0, 1.0])
+    assert list(oracle.topk(c, 4)) == [1, 3, 5, 2]
