@@ -283,7 +283,7 @@ def run_ours(args):
             "roofline": roofline}
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, dt, Sc = cpu_oracle_throughput(ch, targets, cores * 48, cores)
+        v, dt, Sc = cpu_oracle_throughput(ch, targets, cores * 800, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{Sc} rollouts x {STEPS_PER_WINDOW} steps of the same window in {dt:.1f} s on {cores} "
                                           "host threads; CPU restatement (oracle), not PyBullet"}

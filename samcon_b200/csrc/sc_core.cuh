@@ -517,6 +517,72 @@ SC_DEV void response_chain(float *S, const Tables &T, int b, V3 n, V3 f, int col
     for (int i = 0; i < 6; i++) F(O_DA + colofs_a + i) = x[i];
 }
 
+#if defined(__CUDA_ARCH__)
+// Device version of the Gauss-Seidel sweep.  Lane `slot` of a quad owns rows slot, slot+4, ... of its sample's
+// contact system; those rows of the (symmetric) matrix, the residuals and the impulses stay in registers for all
+// iterations, the owner of the updated row broadcasts the impulse change to its quad with one shuffle, and every
+// lane folds it into its residuals.  Rows beyond 3*nc are zero rows and never move.  Same update order and
+// arithmetic as the shared-memory version below (which the host emulation uses).
+template <class TT>
+__device__ __forceinline__ void gs_registers(float *sm, const TT &T, int ncmax) {
+    const int lane = threadIdx.x & 31;
+    float *S = sm + (lane & 7);
+    const int slot = lane >> 3;
+    const int nr = 3 * f2i(F(O_NC));
+    constexpr int RPL = NR / QUAD;     // rows per lane
+    float a[RPL][NR], res[RPL], lam[RPL], dgi[RPL], lamn[MAXC];
+#pragma unroll
+    for (int m = 0; m < RPL; m++) {
+        const int row = slot + QUAD * m;
+        const bool live = row < nr;
+#pragma unroll
+        for (int c = 0; c < NR; c++) {
+            float v = 0.0f;
+            if (c < 3 * ncmax) {
+                const int hi = row > c ? row : c, lo = row > c ? c : row;
+                if (live && c < nr) v = F(O_AM + hi * (hi + 1) / 2 + lo);
+            }
+            a[m][c] = v;
+        }
+        res[m] = live ? F(O_RHS + row) : 0.0f;
+        dgi[m] = live ? 1.0f / F(O_AM + row * (row + 1) / 2 + row) : 0.0f;
+        lam[m] = 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) lamn[c] = 0.0f;
+    for (int it = 0; it < T.niter; it++) {
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++)
+#pragma unroll
+            for (int c = 0; c < MAXC; c++) {
+                if (c >= ncmax) break;
+#pragma unroll
+                for (int k = (pass ? 1 : 0); k < (pass ? 3 : 1); k++) {
+                    const int r = 3 * c + k, owner = r & 3, m = r >> 2;
+                    float d = 0.0f;
+                    if (slot == owner) {
+                        float nl = lam[m] + res[m] * dgi[m];
+                        if (k == 0) nl = fmaxf(nl, 0.0f);
+                        else { const float lim = T.mu * lamn[c]; nl = fminf(lim, fmaxf(-lim, nl)); }
+                        d = nl - lam[m];
+                        lam[m] = nl;
+                    }
+                    d = __shfl_sync(0xffffffffu, d, (lane & 7) + 8 * owner);
+                    if (k == 0) lamn[c] += d;
+#pragma unroll
+                    for (int mm = 0; mm < RPL; mm++) res[mm] -= a[mm][r] * d;
+                }
+            }
+    }
+#pragma unroll
+    for (int m = 0; m < RPL; m++) {
+        const int row = slot + QUAD * m;
+        if (row < nr) F(O_LAM + row) = lam[m];
+    }
+    __syncwarp();
+}
+#endif
+
 template <class TT>
 SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax) {
     // ---- right-hand sides from the predicted velocities -----------------------------------------------------
@@ -593,6 +659,9 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax) {
         SC_SYNC();
     }
     // ---- projected Gauss-Seidel, Bullet row order: all normals, then the friction pairs -------------------------
+#if defined(__CUDA_ARCH__)
+    gs_registers(sm, T, ncmax);
+#else
     SC_STAGE {
         SC_LANE;
         const int nc = f2i(F(O_NC));
@@ -640,6 +709,7 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax) {
         }
         SC_SYNC();
     }
+#endif
     // ---- apply the impulses: one articulated response over the tree ------------------------------------------
     for (int d = T.nlev - 1; d >= 0; d--) {
         SC_STAGE {

@@ -59,8 +59,14 @@ def test_zero_noise_dims_reproduce_target():
 
 
 def _quat_dist(a, b):
-    d = np.abs((a.reshape(-1, 4) * b.reshape(-1, 4)).sum(-1))
-    return 2 * np.arccos(np.clip(d, 0, 1))
+    """rotation angle between quaternion batches, via the vector part of the relative rotation (well conditioned
+    near zero, unlike acos of the dot product of float32-rounded unit quaternions)"""
+    a = np.asarray(a, np.float64).reshape(-1, 4)
+    b = np.asarray(b, np.float64).reshape(-1, 4)
+    a = a / np.linalg.norm(a, axis=1, keepdims=True)
+    b = b / np.linalg.norm(b, axis=1, keepdims=True)
+    v = (b[:, 3:4] * a[:, :3] - a[:, 3:4] * b[:, :3] - np.cross(b[:, :3], a[:, :3]))
+    return 2 * np.arcsin(np.clip(np.linalg.norm(v, axis=1), 0, 1))
 
 
 @pytest.mark.gpu
