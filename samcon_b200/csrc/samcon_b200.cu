@@ -26,8 +26,15 @@ __global__ void __launch_bounds__(32 * WPB) sc_rollout_kernel(const Tables *__re
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *sm = smem + TABLE_WORDS + warp * WORDS_PER_TILE;
     const int ntiles = (a.S + TILE - 1) / TILE;
+#if defined(SC_PROFILE)
+    long long sc_prof_acc[SC_NPHASE] = {}, sc_prof_last = clock64();
+#endif
     for (int tile = blockIdx.x * WPB + warp; tile < ntiles; tile += gridDim.x * WPB)
-        rollout_tile(sm, T, a, tile * TILE, lane, lane + 1);
+        rollout_tile(sm, T, a, tile * TILE, lane, lane + 1 SC_PROF_PASS);
+#if defined(SC_PROFILE)
+    if (lane == 0 && a.prof)
+        for (int i = 0; i < SC_NPHASE; i++) atomicAdd((unsigned long long *)a.prof + i, (unsigned long long)sc_prof_acc[i]);
+#endif
 }
 
 // ============================================================================================================
@@ -197,6 +204,7 @@ struct sc_context {
     int *d_iota; size_t iota_cap;
     int smem_bytes, grid_cap;
     long long launches;
+    long long *d_prof;
     char err[512];
 };
 
@@ -206,7 +214,7 @@ static int sc_fail(sc_context *h, int code, const char *fmt, ...) {
 }
 #define SC_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return sc_fail(h, SC_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
-constexpr int WPB = 1;
+constexpr int WPB = 8;
 
 extern "C" int sc_create(sc_handle *out, const sc_model *model, int device) {
     if (!out) return SC_EINVAL;
@@ -249,6 +257,17 @@ extern "C" int sc_rollout_config(sc_handle h, int *smem_bytes, int *samples_per_
     return SC_OK;
 }
 
+#if defined(SC_PROFILE)
+// developer build only (tools/phase_profile.py): read and reset the per-phase cycle counters
+extern "C" int sc_prof_read(sc_handle h, long long *out16) {
+    if (!h || !h->d_prof) return SC_EINVAL;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out16, h->d_prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemset(h->d_prof, 0, 16 * sizeof(long long));
+    return SC_OK;
+}
+#endif
+
 template <class T>
 static int sc_reserve(sc_context *h, T **p, size_t *cap, size_t need) {
     if (*cap >= need) return SC_OK;
@@ -265,7 +284,14 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a, cudaStream_t s
     const int ntiles = (a.S + TILE - 1) / TILE;
     int grid = (ntiles + WPB - 1) / WPB;
     if (grid > h->grid_cap) grid = h->grid_cap;
+#if defined(SC_PROFILE)
+    RolloutArgs ap = a;
+    if (!h->d_prof) { cudaMalloc(&h->d_prof, 16 * sizeof(long long)); cudaMemset(h->d_prof, 0, 16 * sizeof(long long)); }
+    ap.prof = a.nsteps > 0 ? h->d_prof : nullptr;
+    sc_rollout_kernel<WPB><<<grid, 32 * WPB, h->smem_bytes, st>>>(h->d_tables, ap);
+#else
     sc_rollout_kernel<WPB><<<grid, 32 * WPB, h->smem_bytes, st>>>(h->d_tables, a);
+#endif
     h->launches++;
     SC_CUDA(h, cudaGetLastError());
     return SC_OK;

@@ -27,19 +27,35 @@
 #define SC_SYNC() ((void)0)
 #endif
 
+// Optional phase timing (developer builds only: -DSC_PROFILE, tools/phase_profile.py).  SC_T(i) charges the cycles
+// since the previous mark to phase i of this warp.
+#if defined(SC_PROFILE) && defined(__CUDACC__)
+#define SC_NPHASE 16
+#define SC_T(i) do { long long t_ = clock64(); sc_prof_acc[i] += t_ - sc_prof_last; sc_prof_last = t_; } while (0)
+#define SC_PROF_ARGS , long long *sc_prof_acc, long long &sc_prof_last
+#define SC_PROF_PASS , sc_prof_acc, sc_prof_last
+#else
+#define SC_T(i) ((void)0)
+#define SC_PROF_ARGS
+#define SC_PROF_PASS
+#endif
+
 namespace sc {
 
 constexpr int NB = SC_MAX_BODIES;
 constexpr int MAXLEV = SC_MAX_LEVELS;
 constexpr int MAXC = SC_MAX_CONTACTS;
 constexpr int NR = 3 * MAXC;
-constexpr int TILE = 8;   // samples per warp
-constexpr int QUAD = 4;   // lanes per sample
+constexpr int TILE = 4;   // samples per warp
+constexpr int QUAD = 8;   // lanes per sample (the name predates the 8-lane mapping)
+static_assert(TILE * QUAD == 32, "one tile per warp");
 
 // ---- derived model tables (copied to shared memory once per CTA) ------------------------------------------
 struct Tables {
     int nb, nlev, ncand, ncp, nee, niter, nsub, maxc, nj;
     int parent[NB], depth[NB], jidx[NB], jbody[NB], nchild[NB], child[NB][4], level_start[MAXLEV + 1], anc_mask[NB];
+    int anc[NB][MAXLEV];   // anc[b][d] = ancestor of b at tree depth d (d <= depth[b]; anc[b][depth[b]] = b), else -1
+    int cand_per_lane;
     int cand_body[SC_MAX_CAND], cp_body[SC_MAX_CPOINTS], ee[4];
     float jorg[NB * 3], idyn[NB * 10], ipd[NB * 10], kp[NB], kd[NB], maxf[NB], cand[SC_MAX_CAND * 4];
     float cp_off[SC_MAX_CPOINTS * 3], cp_mass[SC_MAX_CPOINTS], jw[NB], cw[5];
@@ -68,19 +84,26 @@ constexpr int O_CR = O_CB + MAXC;         // contact point relative to body orig
 constexpr int O_CD = O_CR + 3 * MAXC;     // signed distance
 constexpr int O_NC = O_CD + MAXC;         // number of contacts (int)
 constexpr int O_TM = O_NC + 1;            // mask of bodies on a root path of some contact (int)
-constexpr int O_DU = O_TM + 1;            // response pass: u per chain level, 3 columns (9 per level)
-constexpr int O_AM = O_DU + 9 * MAXLEV;   // contact-space matrix, packed lower triangle
-constexpr int O_RHS = O_AM + NR * (NR + 1) / 2;
+constexpr int O_RHS = O_TM + 1;
 constexpr int O_LAM = O_RHS + NR;
-constexpr int O_RES = O_LAM + NR;
+constexpr int O_END_DEV = O_LAM + NR;
+// regions that are only live while O_IC is dead (O_IC is written by the inward ABA sweep and consumed by the end of it)
+constexpr int O_AM = O_IC;                // contact-space matrix, packed lower triangle (contact solve)
+constexpr int O_ZC = O_IC;                // collide: candidate heights ...
+constexpr int O_CNT = O_ZC + SC_MAX_CAND; // ... and hits per lane
+constexpr int O_FEAT = O_RHS;             // end of window: com(3) comvel(3) ee(4x3)
+static_assert(NR * (NR + 1) / 2 <= 21 * NB, "AM must fit in IC");
+static_assert(SC_MAX_CAND + QUAD <= 21 * NB, "ZC + CNT must fit in IC");
+static_assert(18 <= 2 * NR, "FEAT must fit in RHS + LAM");
+#if defined(__CUDACC__)
+constexpr int O_END = O_END_DEV;
+#else
+// host emulation of the Gauss-Seidel sweep keeps its per-row state in (emulated) shared memory
+constexpr int O_RES = O_END_DEV;
 constexpr int O_DGI = O_RES + NR;
 constexpr int O_DEL = O_DGI + NR;         // pending impulse change, double buffered (2)
-constexpr int O_FEAT = O_DEL + 2;         // com(3) comvel(3) ee(4x3)
-constexpr int O_END = O_FEAT + 18;
-constexpr int O_DA = O_IC;                // response pass: accelerations, 3 columns x 6 per body (aliases IC)
-constexpr int O_ZC = O_AM;                // collide: candidate heights (aliases AM)
-static_assert(18 * NB <= 21 * NB, "DA must fit in IC");
-static_assert(SC_MAX_CAND <= NR * (NR + 1) / 2, "ZC must fit in AM");
+constexpr int O_END = O_DEL + 2;
+#endif
 constexpr int WORDS_PER_SAMPLE = O_END;
 constexpr int WORDS_PER_TILE = WORDS_PER_SAMPLE * TILE;
 
@@ -227,11 +250,10 @@ SC_DEV void solve6(const float *L, float *x) {
 
 // max over the 8 samples of a tile of an int field; call between stages only
 SC_DEV int tile_max_int(const float *sm, int off) {
-#if defined(__CUDA_ARCH__)
-    int v = f2i(sm[off * TILE + (threadIdx.x & 7)]);
-    v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
-    v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
-    v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+#if defined(__CUDACC__)
+    int v = f2i(sm[off * TILE + (threadIdx.x & (TILE - 1))]);
+#pragma unroll
+    for (int o = 1; o < TILE; o <<= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 #else
     int v = f2i(sm[off * TILE]);
@@ -241,7 +263,7 @@ SC_DEV int tile_max_int(const float *sm, int off) {
 }
 
 #define SC_STAGE for (int lane = L0; lane < L1; ++lane)
-#define SC_LANE float *S = sm + (lane & 7); const int slot = lane >> 3; (void)slot; (void)S
+#define SC_LANE float *S = sm + (lane & (sc::TILE - 1)); const int slot = lane / sc::TILE; (void)slot; (void)S
 
 // ============================================================================================================
 // kinematics
@@ -447,21 +469,64 @@ SC_DEV void pd_term_body(float *S, const Tables &T, int b, const float *act) {
 SC_DEV V3 cdir(const M3 &R, int k) { return k == 0 ? row(R, 2) : (k == 1 ? neg(row(R, 1)) : row(R, 0)); }
 SC_DEV float cproj(V3 w, int k) { return k == 0 ? w.z : (k == 1 ? -w.y : w.x); }
 
+// Candidate points (sphere centres with a radius, box corners with radius 0) against the plane z = 0.
+// Stage 1: the lanes of a sample test contiguous chunks of the candidate list and count their hits.
+// Stage 2: with the counts of the lower lanes as offset every lane appends its hits, so the contact list is in
+// candidate order; only when more than `maxc` points are inside the margin does lane 0 pick the deepest serially.
+constexpr int CAND_PER_LANE_MAX = (SC_MAX_CAND + QUAD - 1) / QUAD;
+
+SC_DEV void write_contact(float *S, const Tables &T, int j, int c, float z) {
+    const int b = T.cand_body[c];
+    const float *pt = T.cand + 4 * c;
+    F(O_CB + j) = i2f(b);
+    F(O_CR + 3 * j) = pt[0] - pt[3] * F(O_RW + 9 * b + 6);
+    F(O_CR + 3 * j + 1) = pt[1] - pt[3] * F(O_RW + 9 * b + 7);
+    F(O_CR + 3 * j + 2) = pt[2] - pt[3] * F(O_RW + 9 * b + 8);
+    F(O_CD + j) = z;
+}
+
 template <class TT>
 SC_DEV void collide(float *sm, const TT &T, int L0, int L1) {
     SC_STAGE {
         SC_LANE;
-        for (int c = slot; c < T.ncand; c += QUAD) {
-            const int b = T.cand_body[c];
-            const float *pt = T.cand + 4 * c;
-            F(O_ZC + c) = F(O_PW + 3 * b + 2) + F(O_RW + 9 * b + 6) * pt[0] + F(O_RW + 9 * b + 7) * pt[1] +
-                          F(O_RW + 9 * b + 8) * pt[2] - pt[3];
+        const int c0 = slot * T.cand_per_lane;
+        int hits = 0;
+#pragma unroll
+        for (int i = 0; i < CAND_PER_LANE_MAX; i++) {
+            const int c = c0 + i;
+            if (i < T.cand_per_lane && c < T.ncand) {
+                const int b = T.cand_body[c];
+                const float *pt = T.cand + 4 * c;
+                const float z = F(O_PW + 3 * b + 2) + F(O_RW + 9 * b + 6) * pt[0] + F(O_RW + 9 * b + 7) * pt[1] +
+                                F(O_RW + 9 * b + 8) * pt[2] - pt[3];
+                F(O_ZC + c) = z;
+                hits += z < T.cthresh ? 1 : 0;
+            }
         }
+        F(O_CNT + slot) = i2f(hits);
     }
     SC_SYNC();
     SC_STAGE {
         SC_LANE;
-        if (slot == 0) {
+        int ofs = 0, total = 0;
+#pragma unroll
+        for (int l = 0; l < QUAD; l++) {
+            const int n = f2i(F(O_CNT + l));
+            ofs += l < slot ? n : 0;
+            total += n;
+        }
+        if (total <= T.maxc) {
+            const int c0 = slot * T.cand_per_lane;
+            if (f2i(F(O_CNT + slot)) > 0)
+                for (int i = 0; i < T.cand_per_lane; i++) {
+                    const int c = c0 + i;
+                    if (c < T.ncand) {
+                        const float z = F(O_ZC + c);
+                        if (z < T.cthresh) write_contact(S, T, ofs++, c, z);
+                    }
+                }
+            if (slot == 0) F(O_NC) = i2f(total);
+        } else if (slot == 0) {
             // O_CB holds candidate indices and O_CD heights while the deepest maxc are being chosen
             int n = 0;
             for (int c = 0; c < T.ncand; c++) {
@@ -476,98 +541,118 @@ SC_DEV void collide(float *sm, const TT &T, int L0, int L1) {
                     F(O_CB + n - 1) = i2f(c); F(O_CD + n - 1) = z;
                 }
             }
-            int mask = 0;
-            for (int j = 0; j < n; j++) {
-                const int c = f2i(F(O_CB + j)), b = T.cand_body[c];
-                const float *pt = T.cand + 4 * c;
-                F(O_CB + j) = i2f(b);
-                F(O_CR + 3 * j) = pt[0] - pt[3] * F(O_RW + 9 * b + 6);
-                F(O_CR + 3 * j + 1) = pt[1] - pt[3] * F(O_RW + 9 * b + 7);
-                F(O_CR + 3 * j + 2) = pt[2] - pt[3] * F(O_RW + 9 * b + 8);
-                mask |= T.anc_mask[b];
-            }
+            for (int j = 0; j < n; j++) write_contact(S, T, j, f2i(F(O_CB + j)), F(O_CD + j));
             F(O_NC) = i2f(n);
-            F(O_TM) = i2f(mask);
         }
     }
     SC_SYNC();
 }
 
-// one column of the articulated response: walk a spatial force on `b` (body coords) up to the root,
-// recording u per level, and solve the base.  Runs inside one lane (no barrier needed).
-SC_DEV void response_chain(float *S, const Tables &T, int b, V3 n, V3 f, int colofs_u, int colofs_a) {
-    V3 pn = neg(n), pf = neg(f);
-    while (b != 0) {
-        const V3 u = neg(pn);
-        st3(S, O_DU + 9 * T.depth[b] + colofs_u, u);
-        const V3 Ku = mul(ldS(S, O_DI + 6 * b), u);
-        pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
-        pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
-        const M3 Rj = ldRj(S, b);
-        const V3 fp = mul(Rj, pf);
-        pn = mul(Rj, pn) + cross(tv3(T.jorg, b), fp);
-        pf = fp;
-        b = T.parent[b];
+// One column of the contact-space matrix A = J M^-1 J^T, computed by one lane without barriers: the response of
+// the articulated system (inertias left in shared memory by the dynamics ABA) to a unit impulse along direction k
+// of contact j.  The impulse walks up the tree to the root (recording u = -S^T p per level in registers), the 6x6
+// base block is solved with the Cholesky factor kept from the ABA, and accelerations walk back down to the bodies
+// of the contacts i >= j; rows >= the column index land in the packed lower triangle O_AM.
+SC_DEV void contact_column(float *S, const Tables &T, int nc, int c) {
+    const int j = c / 3, k = c - 3 * j;
+    const int bj = f2i(F(O_CB + j)), dj = T.depth[bj];
+    const V3 f = cdir(ldM(S, O_RW + 9 * bj), k);
+    V3 pn = neg(cross(ld3(S, O_CR + 3 * j), f)), pf = neg(f);
+    V3 u[MAXLEV];
+#pragma unroll
+    for (int d = MAXLEV - 1; d >= 1; d--) {
+        u[d] = mk(0, 0, 0);
+        if (d <= dj) {
+            const int b = T.anc[bj][d];
+            u[d] = neg(pn);
+            const V3 Ku = mul(ldS(S, O_DI + 6 * b), u[d]);
+            pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
+            pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
+            const M3 Rj = ldRj(S, b);
+            const V3 fp = mul(Rj, pf);
+            pn = mul(Rj, pn) + cross(tv3(T.jorg, b), fp);
+            pf = fp;
+        }
     }
     float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
 #pragma unroll
     for (int i = 0; i < 21; i++) L[i] = F(O_I0L + i);
     solve6(L, x);
+    int bprev = -1;
+    V3 aw = mk(0, 0, 0), al = mk(0, 0, 0);
+    for (int i = j; i < nc; i++) {
+        const int bi = f2i(F(O_CB + i));
+        if (bi != bprev) {
+            bprev = bi;
+            const int di = T.depth[bi];
+            aw = mk(x[0], x[1], x[2]); al = mk(x[3], x[4], x[5]);
 #pragma unroll
-    for (int i = 0; i < 6; i++) F(O_DA + colofs_a + i) = x[i];
+            for (int d = 1; d < MAXLEV; d++) {
+                if (d <= di) {
+                    const int b = T.anc[bi][d];
+                    const M3 Rj = ldRj(S, b);
+                    const V3 pw = mulT(Rj, aw), pl = mulT(Rj, al + cross(aw, tv3(T.jorg, b)));
+                    const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);
+                    const V3 qdd = mul(ldS(S, O_DI + 6 * b), uu - mul(ldS(S, O_UA + 6 * b), pw) - mulT(ldM(S, O_UB + 9 * b), pl));
+                    aw = pw + qdd; al = pl;
+                }
+            }
+        }
+        const V3 a = mul(ldM(S, O_RW + 9 * bi), al + cross(aw, ld3(S, O_CR + 3 * i)));
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) {
+            const int rr = 3 * i + kk;
+            if (rr >= c) F(O_AM + rr * (rr + 1) / 2 + c) = cproj(a, kk);
+        }
+    }
 }
 
-#if defined(__CUDA_ARCH__)
-// Device version of the Gauss-Seidel sweep.  Lane `slot` of a quad owns rows slot, slot+4, ... of its sample's
-// contact system; those rows of the (symmetric) matrix, the residuals and the impulses stay in registers for all
-// iterations, the owner of the updated row broadcasts the impulse change to its quad with one shuffle, and every
-// lane folds it into its residuals.  Rows beyond 3*nc are zero rows and never move.  Same update order and
-// arithmetic as the shared-memory version below (which the host emulation uses).
-template <class TT>
-__device__ __forceinline__ void gs_registers(float *sm, const TT &T, int ncmax) {
+#if defined(__CUDACC__)
+// Device version of the Gauss-Seidel sweep.  Lane `slot` of a sample owns rows slot, slot+QUAD, ... of its contact
+// system; those rows of the (symmetric) matrix, the residuals and the impulses stay in registers for all
+// iterations, the owner of the updated row broadcasts the impulse change to the sample's lanes with one shuffle,
+// and every lane folds it into its residuals.  Rows beyond 3*nc are zero rows and never move.  NCT = contacts the
+// sweep is unrolled for (>= the tile's largest count), so the control flow is uniform and branch free.
+template <int NCT, class TT>
+__device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
     const int lane = threadIdx.x & 31;
-    float *S = sm + (lane & 7);
-    const int slot = lane >> 3;
+    float *S = sm + (lane & (TILE - 1));
+    const int slot = lane / TILE;
     const int nr = 3 * f2i(F(O_NC));
-    constexpr int RPL = NR / QUAD;     // rows per lane
-    float a[RPL][NR], res[RPL], lam[RPL], dgi[RPL], lamn[MAXC];
+    constexpr int NRT = 3 * NCT, RPL = (NRT + QUAD - 1) / QUAD;     // rows per lane
+    float a[RPL][NRT], res[RPL], lam[RPL], dgi[RPL], lamn[NCT];
 #pragma unroll
     for (int m = 0; m < RPL; m++) {
         const int row = slot + QUAD * m;
         const bool live = row < nr;
 #pragma unroll
-        for (int c = 0; c < NR; c++) {
-            float v = 0.0f;
-            if (c < 3 * ncmax) {
-                const int hi = row > c ? row : c, lo = row > c ? c : row;
-                if (live && c < nr) v = F(O_AM + hi * (hi + 1) / 2 + lo);
-            }
-            a[m][c] = v;
+        for (int c = 0; c < NRT; c++) {
+            const int hi = row > c ? row : c, lo = row > c ? c : row;
+            a[m][c] = (live && c < nr) ? F(O_AM + hi * (hi + 1) / 2 + lo) : 0.0f;
         }
         res[m] = live ? F(O_RHS + row) : 0.0f;
         dgi[m] = live ? 1.0f / F(O_AM + row * (row + 1) / 2 + row) : 0.0f;
         lam[m] = 0.0f;
     }
 #pragma unroll
-    for (int c = 0; c < MAXC; c++) lamn[c] = 0.0f;
+    for (int c = 0; c < NCT; c++) lamn[c] = 0.0f;
+    const float mu = T.mu;
+    const int src0 = lane & (TILE - 1);
     for (int it = 0; it < T.niter; it++) {
 #pragma unroll
         for (int pass = 0; pass < 2; pass++)
 #pragma unroll
-            for (int c = 0; c < MAXC; c++) {
-                if (c >= ncmax) break;
+            for (int c = 0; c < NCT; c++) {
 #pragma unroll
                 for (int k = (pass ? 1 : 0); k < (pass ? 3 : 1); k++) {
-                    const int r = 3 * c + k, owner = r & 3, m = r >> 2;
-                    float d = 0.0f;
-                    if (slot == owner) {
-                        float nl = lam[m] + res[m] * dgi[m];
-                        if (k == 0) nl = fmaxf(nl, 0.0f);
-                        else { const float lim = T.mu * lamn[c]; nl = fminf(lim, fmaxf(-lim, nl)); }
-                        d = nl - lam[m];
-                        lam[m] = nl;
-                    }
-                    d = __shfl_sync(0xffffffffu, d, (lane & 7) + 8 * owner);
+                    constexpr int dummy = 0; (void)dummy;
+                    const int r = 3 * c + k, owner = r % QUAD, m = r / QUAD;
+                    float nl = lam[m] + res[m] * dgi[m];
+                    const float lim = k == 0 ? 3.0e38f : mu * lamn[c];
+                    nl = fminf(lim, fmaxf(k == 0 ? 0.0f : -lim, nl));
+                    float d = slot == owner ? nl - lam[m] : 0.0f;
+                    if (slot == owner) lam[m] = nl;
+                    d = __shfl_sync(0xffffffffu, d, src0 + TILE * owner);
                     if (k == 0) lamn[c] += d;
 #pragma unroll
                     for (int mm = 0; mm < RPL; mm++) res[mm] -= a[mm][r] * d;
@@ -584,8 +669,8 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T, int ncmax) 
 #endif
 
 template <class TT>
-SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax) {
-    // ---- right-hand sides from the predicted velocities -----------------------------------------------------
+SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_PROF_ARGS) {
+    // ---- right-hand sides from the predicted velocities; mask of the bodies on a contact's root path ------------
     SC_STAGE {
         SC_LANE;
         const int nc = f2i(F(O_NC));
@@ -599,68 +684,32 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax) {
             F(O_RHS + 3 * j + 2) = -vp.x;
             F(O_LAM + 3 * j) = 0; F(O_LAM + 3 * j + 1) = 0; F(O_LAM + 3 * j + 2) = 0;
         }
+        if (slot == QUAD - 1) {
+            int mask = 0;
+            for (int j = 0; j < nc; j++) mask |= T.anc_mask[f2i(F(O_CB + j))];
+            F(O_TM) = i2f(mask);
+        }
+#if !defined(__CUDACC__)
         if (slot == 0) { F(O_DEL) = 0; F(O_DEL + 1) = 0; }
+#endif
     }
     SC_SYNC();
-    // ---- contact-space matrix, one contact (3 columns) at a time ----------------------------------------------
-    for (int j = 0; j < ncmax; j++) {
-        SC_STAGE {
-            SC_LANE;
-            const int nc = f2i(F(O_NC));
-            if (j < nc && slot < 3) {
-                const int b = f2i(F(O_CB + j));
-                const V3 f = cdir(ldM(S, O_RW + 9 * b), slot);
-                response_chain(S, T, b, cross(ld3(S, O_CR + 3 * j), f), f, 3 * slot, 6 * slot);
-            }
-        }
-        SC_SYNC();
-        for (int d = 1; d < T.nlev; d++) {
-            SC_STAGE {
-                SC_LANE;
-                const int nc = f2i(F(O_NC));
-                if (j < nc) {
-                    const int mask = f2i(F(O_TM)), chain = T.anc_mask[f2i(F(O_CB + j))];
-                    const int width = T.level_start[d + 1] - T.level_start[d];
-                    for (int it = slot; it < 3 * width; it += QUAD) {
-                        const int b = T.level_start[d] + it / 3, c = it % 3;
-                        if (!((mask >> b) & 1)) continue;
-                        const int p = T.parent[b];
-                        const M3 Rj = ldRj(S, b);
-                        const V3 alp = ld3(S, O_DA + 18 * p + 6 * c), ap = ld3(S, O_DA + 18 * p + 6 * c + 3);
-                        const V3 aw = mulT(Rj, alp), al = mulT(Rj, ap + cross(alp, tv3(T.jorg, b)));
-                        V3 u = mk(0, 0, 0);
-                        if ((chain >> b) & 1) u = ld3(S, O_DU + 9 * d + 3 * c);
-                        const V3 qdd = mul(ldS(S, O_DI + 6 * b), u - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
-                        st3(S, O_DA + 18 * b + 6 * c, aw + qdd);
-                        st3(S, O_DA + 18 * b + 6 * c + 3, al);
-                    }
-                }
-            }
-            SC_SYNC();
-        }
-        SC_STAGE {
-            SC_LANE;
-            const int nc = f2i(F(O_NC));
-            if (j < nc) {
-                for (int it = 3 * j + slot; it < 3 * nc; it += QUAD) {
-                    const int i = it / 3, c = it % 3;
-                    const int b = f2i(F(O_CB + i));
-                    const V3 a = ld3(S, O_DA + 18 * b + 6 * c + 3) + cross(ld3(S, O_DA + 18 * b + 6 * c), ld3(S, O_CR + 3 * i));
-                    const V3 aw = mul(ldM(S, O_RW + 9 * b), a);
-                    const int cc = 3 * j + c;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const int rr = 3 * i + k;
-                        if (rr >= cc) F(O_AM + rr * (rr + 1) / 2 + cc) = cproj(aw, k);
-                    }
-                }
-            }
-        }
-        SC_SYNC();
+    SC_T(7);
+    // ---- contact-space matrix: the lanes of a sample take its columns round-robin, no barriers in between --------
+    SC_STAGE {
+        SC_LANE;
+        const int nc = f2i(F(O_NC));
+        for (int c = slot; c < 3 * nc; c += QUAD) contact_column(S, T, nc, c);
     }
+    SC_SYNC();
+    SC_T(8);
     // ---- projected Gauss-Seidel, Bullet row order: all normals, then the friction pairs -------------------------
-#if defined(__CUDA_ARCH__)
-    gs_registers(sm, T, ncmax);
+#if defined(__CUDACC__)
+    if (ncmax <= 2) gs_registers<2>(sm, T);
+    else if (ncmax <= 4) gs_registers<4>(sm, T);
+    else if (ncmax <= 6) gs_registers<6>(sm, T);
+    else gs_registers<8>(sm, T);
+    SC_T(9);
 #else
     SC_STAGE {
         SC_LANE;
@@ -696,7 +745,7 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax) {
                 if (c < nc) {
                     const int k = tl < ncmax ? 0 : 1 + ((tl - ncmax) & 1);
                     const int r = 3 * c + k;
-                    if ((r & 3) == slot) {
+                    if ((r % QUAD) == slot) {
                         const float lam = F(O_LAM + r);
                         float nl = lam + F(O_RES + r) * F(O_DGI + r);
                         if (k == 0) nl = fmaxf(nl, 0.0f);
@@ -836,7 +885,7 @@ template <class TT>
 SC_DEV void load_state(float *sm, const TT &T, int L0, int L1, const float *rows, const int *parent_idx, int children, int tile0, int S_total) {
     SC_STAGE {
         SC_LANE;
-        int k = tile0 + (lane & 7);
+        int k = tile0 + (lane & (TILE - 1));
         if (k >= S_total) k = S_total - 1;   // padding lanes replay the last sample and never write
         const float *src = rows + (size_t)(parent_idx ? parent_idx[k] : k / children) * SC_STATE_DIM;
         for (int i = slot; i < SC_STATE_DIM; i += QUAD) F(state_word(T, i)) = src[i];
@@ -938,38 +987,49 @@ struct RolloutArgs {
     float *out_state, *out_cost, *out_info;   // any may be null
     float *out_feat;           // [S,18] or null (feature-only mode)
     float *out_cost6;          // [S,6] total + 5 terms, or null (sc_cost)
+    long long *prof;           // developer builds (-DSC_PROFILE): per-phase cycle counters, else null
 };
 
 template <class TT>
-SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0, int L0, int L1) {
+SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0, int L0, int L1 SC_PROF_ARGS) {
+    SC_T(15);
     load_state(sm, T, L0, L1, a.parents, a.parent_idx, a.children, tile0, a.S);
+    SC_T(0);
     for (int step = 0; step < a.nsteps; step++) {
         fk_sweep(sm, T, L0, L1, true);
+        SC_T(1);
         SC_STAGE {
             SC_LANE;
-            int k = tile0 + (lane & 7);
+            int k = tile0 + (lane & (TILE - 1));
             if (k >= a.S) k = a.S - 1;
             const float *act = a.actions + (size_t)k * (4 * T.nj);
             for (int b = 1 + slot; b < T.nb; b += QUAD) pd_term_body(S, T, b, act);
         }
         SC_SYNC();
+        SC_T(2);
         aba<true>(sm, T, L0, L1);
+        SC_T(3);
         for (int sub = 0; sub < T.nsub; sub++) {
-            if (sub) fk_sweep(sm, T, L0, L1, true);
+            if (sub) { fk_sweep(sm, T, L0, L1, true); SC_T(1); }
             collide(sm, T, L0, L1);
+            SC_T(4);
             aba<false>(sm, T, L0, L1);
+            SC_T(5);
             const int ncmax = tile_max_int(sm, O_NC);
             if (ncmax > 0) {
                 fk_sweep(sm, T, L0, L1, false);
-                contact_solve(sm, T, L0, L1, ncmax);
+                SC_T(6);
+                contact_solve(sm, T, L0, L1, ncmax SC_PROF_PASS);
+                SC_T(10);
             }
             integrate(sm, T, L0, L1);
+            SC_T(11);
         }
     }
     features(sm, T, L0, L1);
     SC_STAGE {
         SC_LANE;
-        const int s = lane & 7, k = tile0 + s;
+        const int s = lane & (TILE - 1), k = tile0 + s;
         if (k < a.S) {
             if (a.out_state) {
                 float *dst = a.out_state + (size_t)k * SC_STATE_DIM;
@@ -987,6 +1047,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
         }
     }
     SC_SYNC();
+    SC_T(12);
 }
 
 }  // namespace sc

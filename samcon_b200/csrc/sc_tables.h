@@ -24,7 +24,7 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
     if (T->level_start[0] != 0 || T->level_start[1] != 1 || T->level_start[m->nlev] != m->nb) SC_FAIL("bad level_start");
     for (int d = 0; d < m->nlev; d++) {
         int w = T->level_start[d + 1] - T->level_start[d];
-        if (w < 1 || w > QUAD) SC_FAIL("tree level %d has %d bodies (1..%d supported)", d, w, QUAD);
+        if (w < 1 || w > 4) SC_FAIL("tree level %d has %d bodies (1..4 supported)", d, w);
     }
     for (int b = 0; b < m->nb; b++) {
         int p = m->parent[b];
@@ -33,6 +33,7 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
         T->depth[b] = b ? T->depth[p] + 1 : 0;
         if (b < T->level_start[T->depth[b]] || b >= T->level_start[T->depth[b] + 1]) SC_FAIL("body %d not in its level", b);
         T->anc_mask[b] = (1 << b) | (b ? T->anc_mask[p] : 0);
+        for (int d = 0; d < MAXLEV; d++) T->anc[b][d] = d < T->depth[b] ? T->anc[p][d] : (d == T->depth[b] ? b : -1);
         if (b) {
             if (T->nchild[p] >= 4) SC_FAIL("body %d has more than 4 children", p);
             T->child[p][T->nchild[p]++] = b;
@@ -44,6 +45,7 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
         for (int k = 0; k < 10; k++) { T->idyn[10 * b + k] = m->inertia_dyn[10 * b + k]; T->ipd[10 * b + k] = m->inertia_pd[10 * b + k]; }
         T->kp[b] = m->kp[b]; T->kd[b] = m->kd[b]; T->maxf[b] = m->maxf[b]; T->jw[b] = m->joint_weights[b];
     }
+    T->cand_per_lane = (m->ncand + QUAD - 1) / QUAD;
     for (int c = 0; c < m->ncand; c++) {
         if (m->cand_body[c] < 0 || m->cand_body[c] >= m->nb) SC_FAIL("bad cand_body");
         T->cand_body[c] = m->cand_body[c];
