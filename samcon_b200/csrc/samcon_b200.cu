@@ -29,8 +29,9 @@ __global__ void __launch_bounds__(32 * WPB) sc_rollout_kernel(const Tables *__re
 #if defined(SC_PROFILE)
     long long sc_prof_acc[SC_NPHASE] = {}, sc_prof_last = clock64();
 #endif
-    for (int tile = blockIdx.x * WPB + warp; tile < ntiles; tile += gridDim.x * WPB)
-        rollout_tile(sm, T, a, tile * TILE, lane, lane + 1 SC_PROF_PASS);
+    // every warp of the CTA runs the same number of rounds (rollout_tile has CTA-wide phase barriers)
+    for (int base = blockIdx.x * WPB; base < ntiles; base += gridDim.x * WPB)
+        rollout_tile(sm, T, a, (base + warp) * TILE, lane, lane + 1 SC_PROF_PASS);
 #if defined(SC_PROFILE)
     if (lane == 0 && a.prof)
         for (int i = 0; i < SC_NPHASE; i++) atomicAdd((unsigned long long *)a.prof + i, (unsigned long long)sc_prof_acc[i]);
@@ -259,11 +260,11 @@ extern "C" int sc_rollout_config(sc_handle h, int *smem_bytes, int *samples_per_
 
 #if defined(SC_PROFILE)
 // developer build only (tools/phase_profile.py): read and reset the per-phase cycle counters
-extern "C" int sc_prof_read(sc_handle h, long long *out16) {
+extern "C" int sc_prof_read(sc_handle h, long long *out) {
     if (!h || !h->d_prof) return SC_EINVAL;
     cudaDeviceSynchronize();
-    cudaMemcpy(out16, h->d_prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaMemset(h->d_prof, 0, 16 * sizeof(long long));
+    cudaMemcpy(out, h->d_prof, SC_NPHASE * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long));
     return SC_OK;
 }
 #endif
@@ -286,7 +287,7 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a, cudaStream_t s
     if (grid > h->grid_cap) grid = h->grid_cap;
 #if defined(SC_PROFILE)
     RolloutArgs ap = a;
-    if (!h->d_prof) { cudaMalloc(&h->d_prof, 16 * sizeof(long long)); cudaMemset(h->d_prof, 0, 16 * sizeof(long long)); }
+    if (!h->d_prof) { cudaMalloc(&h->d_prof, SC_NPHASE * sizeof(long long)); cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long)); }
     ap.prof = a.nsteps > 0 ? h->d_prof : nullptr;
     sc_rollout_kernel<WPB><<<grid, 32 * WPB, h->smem_bytes, st>>>(h->d_tables, ap);
 #else

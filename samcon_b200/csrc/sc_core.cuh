@@ -22,15 +22,21 @@
 #if defined(__CUDACC__)
 #define SC_DEV __device__ __forceinline__
 #define SC_SYNC() __syncwarp()
+// CTA-wide phase alignment.  Not needed for correctness (warps never share data): it keeps the warps of a CTA in
+// the same code region, because the step loop is ~170 KB of SASS and 8 warps at 8 different places in it starve
+// on instruction fetch (ncu: stalled_no_instruction 7.7 per issue on the walk workload without it, 0.2 with the
+// warps aligned).  Every warp of the CTA must execute the same number of these, see rollout_tile().
+#define SC_CTA_SYNC() __syncthreads()
 #else
 #define SC_DEV static inline
 #define SC_SYNC() ((void)0)
+#define SC_CTA_SYNC() ((void)0)
 #endif
 
 // Optional phase timing (developer builds only: -DSC_PROFILE, tools/phase_profile.py).  SC_T(i) charges the cycles
 // since the previous mark to phase i of this warp.
 #if defined(SC_PROFILE) && defined(__CUDACC__)
-#define SC_NPHASE 16
+#define SC_NPHASE 32
 #define SC_T(i) do { long long t_ = clock64(); sc_prof_acc[i] += t_ - sc_prof_last; sc_prof_last = t_; } while (0)
 #define SC_PROF_ARGS , long long *sc_prof_acc, long long &sc_prof_last
 #define SC_PROF_PASS , sc_prof_acc, sc_prof_last
@@ -486,7 +492,7 @@ SC_DEV void write_contact(float *S, const Tables &T, int j, int c, float z) {
 }
 
 template <class TT>
-SC_DEV void collide(float *sm, const TT &T, int L0, int L1) {
+SC_DEV void collide(float *sm, const TT &T, int L0, int L1 SC_PROF_ARGS) {
     SC_STAGE {
         SC_LANE;
         const int c0 = slot * T.cand_per_lane;
@@ -515,6 +521,10 @@ SC_DEV void collide(float *sm, const TT &T, int L0, int L1) {
             ofs += l < slot ? n : 0;
             total += n;
         }
+#if defined(SC_PROFILE) && defined(__CUDACC__)
+        if (total > T.maxc) sc_prof_acc[23]++;
+        sc_prof_acc[24] += total < T.maxc ? total : T.maxc;
+#endif
         if (total <= T.maxc) {
             const int c0 = slot * T.cand_per_lane;
             if (f2i(F(O_CNT + slot)) > 0)
@@ -993,9 +1003,19 @@ struct RolloutArgs {
 template <class TT>
 SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0, int L0, int L1 SC_PROF_ARGS) {
     SC_T(15);
+    if (tile0 >= a.S) {
+        // a warp without a tile in this round only keeps the CTA's phase barriers company
+        for (int step = 0; step < a.nsteps; step++) {
+            SC_CTA_SYNC();
+            for (int sub = 0; sub < T.nsub; sub++) { SC_CTA_SYNC(); SC_CTA_SYNC(); SC_CTA_SYNC(); }
+        }
+        return;
+    }
     load_state(sm, T, L0, L1, a.parents, a.parent_idx, a.children, tile0, a.S);
     SC_T(0);
     for (int step = 0; step < a.nsteps; step++) {
+        SC_CTA_SYNC();
+        SC_T(13);
         fk_sweep(sm, T, L0, L1, true);
         SC_T(1);
         SC_STAGE {
@@ -1010,18 +1030,27 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
         aba<true>(sm, T, L0, L1);
         SC_T(3);
         for (int sub = 0; sub < T.nsub; sub++) {
+            SC_CTA_SYNC();
+            SC_T(13);
             if (sub) { fk_sweep(sm, T, L0, L1, true); SC_T(1); }
-            collide(sm, T, L0, L1);
+            collide(sm, T, L0, L1 SC_PROF_PASS);
             SC_T(4);
             aba<false>(sm, T, L0, L1);
             SC_T(5);
+            SC_CTA_SYNC();
+            SC_T(13);
             const int ncmax = tile_max_int(sm, O_NC);
+#if defined(SC_PROFILE) && defined(__CUDACC__)
+            sc_prof_acc[16]++; sc_prof_acc[17] += ncmax > 0; sc_prof_acc[18 + (ncmax + 1) / 2]++;
+#endif
             if (ncmax > 0) {
                 fk_sweep(sm, T, L0, L1, false);
                 SC_T(6);
                 contact_solve(sm, T, L0, L1, ncmax SC_PROF_PASS);
                 SC_T(10);
             }
+            SC_CTA_SYNC();
+            SC_T(13);
             integrate(sm, T, L0, L1);
             SC_T(11);
         }
