@@ -60,6 +60,7 @@ static_assert(TILE * QUAD == 32, "one tile per warp");
 struct Tables {
     int nb, nlev, ncand, ncp, nee, niter, nsub, maxc, nj;
     int parent[NB], depth[NB], jidx[NB], jbody[NB], nchild[NB], child[NB][4], level_start[MAXLEV + 1], anc_mask[NB];
+    int icslot[NB];        // O_IC slot of body b: (depth & 1) * ICW + position in its level
     int anc[NB][MAXLEV];   // anc[b][d] = ancestor of b at tree depth d (d <= depth[b]; anc[b][depth[b]] = b), else -1
     int cand_per_lane;
     int cand_body[SC_MAX_CAND], cp_body[SC_MAX_CPOINTS], ee[4];
@@ -69,37 +70,44 @@ struct Tables {
 };
 
 // ---- per-sample shared-memory layout (32-bit words) --------------------------------------------------------
-constexpr int O_P0 = 0;                   // root position (3)
-constexpr int O_Q = O_P0 + 3;             // quaternions xyzw: body 0 = root orientation, b>0 = joint rotation
-constexpr int O_VB = O_Q + 4 * NB;        // base world velocity: angular(3), linear(3)
-constexpr int O_W = O_VB + 6;             // joint angular velocity in child frame (3 per body, slot 0 unused)
-constexpr int O_RW = O_W + 3 * NB;        // world rotation per body (9)
-constexpr int O_PW = O_RW + 9 * NB;       // world position of body origin (3)
-constexpr int O_TW = O_PW + 3 * NB;       // body twist in body coords: ang(3), lin(3)
-constexpr int O_TAU = O_TW + 6 * NB;      // joint torque held over the sub-steps (3)
-constexpr int O_IC = O_TAU + 3 * NB;      // articulated-inertia contribution to the parent: A(6) B(9) C(6)
-constexpr int O_PC = O_IC + 21 * NB;      // bias-force contribution to the parent (6); later: accelerations
-constexpr int O_UA = O_PC + 6 * NB;       // articulated inertia, angular block (sym 6)
-constexpr int O_UB = O_UA + 6 * NB;       // articulated inertia, linear-from-angular block (9)
-constexpr int O_DI = O_UB + 9 * NB;       // (S^T IA S + armature)^-1 (sym 6)
-constexpr int O_UU = O_DI + 6 * NB;       // u = tau - S^T pA (3)
-constexpr int O_I0L = O_UU + 3 * NB;      // Cholesky factor of the base articulated inertia (21)
-constexpr int O_TP = O_I0L + 21;          // PD: Kp*err - Kd*w (3); contact apply: -S^T pa (3)
-constexpr int O_CB = O_TP + 3 * NB;       // contact body (int)
-constexpr int O_CR = O_CB + MAXC;         // contact point relative to body origin, body coords (3)
-constexpr int O_CD = O_CR + 3 * MAXC;     // signed distance
-constexpr int O_NC = O_CD + MAXC;         // number of contacts (int)
-constexpr int O_TM = O_NC + 1;            // mask of bodies on a root path of some contact (int)
+// Regions marked (b>=1) have no slot for the root: their offset is pulled back by one stride so that
+// `O_X + stride * b` still addresses body b; the root's would-be slot overlaps the tail of the region before it and is
+// never touched (every per-body loop below treats b == 0 separately).
+constexpr int ICW = 4;                            // articulated-inertia slots per tree level (max level width)
+constexpr int O_P0 = 0;                           // root position (3)
+constexpr int O_Q = O_P0 + 3;                     // quaternions xyzw: body 0 = root orientation, b>0 = joint rotation
+constexpr int O_VB = O_Q + 4 * NB;                // base world velocity: angular(3), linear(3)
+constexpr int O_W = O_VB + 6 - 3;                 // joint angular velocity in child frame (3, b>=1)
+constexpr int O_RW = O_W + 3 * NB;                // world rotation per body (9)
+constexpr int O_PW = O_RW + 9 * NB;               // world position of body origin (3)
+constexpr int O_TW = O_PW + 3 * NB;               // body twist in body coords: ang(3), lin(3)
+constexpr int O_TAU = O_TW + 6 * NB - 3;          // joint torque held over the sub-steps (3, b>=1)
+constexpr int O_UA = O_TAU + 3 * NB - 6;          // articulated inertia, angular block (sym 6, b>=1)
+constexpr int O_UB = O_UA + 6 * NB - 9;           // articulated inertia, linear-from-angular block (9, b>=1)
+constexpr int O_DI = O_UB + 9 * NB - 6;           // (S^T IA S + armature)^-1 (sym 6, b>=1)
+constexpr int O_I0L = O_DI + 6 * NB;              // Cholesky factor of the base articulated inertia (21)
+// scratch block: O_IC .. O_SCR_END is contiguous; the contact-space matrix O_AM overlays all of it while none of
+// its members is live (between the end of the dynamics ABA and the start of the impulse application)
+constexpr int O_IC = O_I0L + 21;                  // articulated-inertia contribution to the parent, A(6) B(9) C(6):
+                                                  // one slot per body of two adjacent tree levels (T.icslot)
+constexpr int O_PC = O_IC + 21 * 2 * ICW;         // bias-force contribution to the parent (6); later: accelerations
+constexpr int O_UU = O_PC + 6 * NB - 3;           // u = tau - S^T pA (3, b>=1); contact apply: -S^T pa
+constexpr int O_TP = O_UU + 3 * NB - 3;           // PD: Kp*err - Kd*w (3, b>=1)
+constexpr int O_SCR_END = O_TP + 3 * NB;
+constexpr int O_CB = O_SCR_END;                   // contact body (int)
+constexpr int O_CR = O_CB + MAXC;                 // contact point relative to body origin, body coords (3)
+constexpr int O_CD = O_CR + 3 * MAXC;             // signed distance
+constexpr int O_NC = O_CD + MAXC;                 // number of contacts (int)
+constexpr int O_TM = O_NC + 1;                    // mask of bodies on a root path of some contact (int)
 constexpr int O_RHS = O_TM + 1;
 constexpr int O_LAM = O_RHS + NR;
 constexpr int O_END_DEV = O_LAM + NR;
-// regions that are only live while O_IC is dead (O_IC is written by the inward ABA sweep and consumed by the end of it)
-constexpr int O_AM = O_IC;                // contact-space matrix, packed lower triangle (contact solve)
-constexpr int O_ZC = O_IC;                // collide: candidate heights ...
-constexpr int O_CNT = O_ZC + SC_MAX_CAND; // ... and hits per lane
-constexpr int O_FEAT = O_RHS;             // end of window: com(3) comvel(3) ee(4x3)
-static_assert(NR * (NR + 1) / 2 <= 21 * NB, "AM must fit in IC");
-static_assert(SC_MAX_CAND + QUAD <= 21 * NB, "ZC + CNT must fit in IC");
+constexpr int O_AM = O_IC;                        // contact-space matrix, packed lower triangle (contact solve)
+constexpr int O_ZC = O_IC;                        // collide: candidate heights ...
+constexpr int O_CNT = O_ZC + SC_MAX_CAND;         // ... and hits per lane
+constexpr int O_FEAT = O_RHS;                     // end of window: com(3) comvel(3) ee(4x3)
+static_assert(NR * (NR + 1) / 2 <= O_SCR_END - O_IC, "AM must fit in the scratch block");
+static_assert(SC_MAX_CAND + QUAD <= 21 * 2 * ICW, "ZC + CNT must fit in IC");
 static_assert(18 <= 2 * NR, "FEAT must fit in RHS + LAM");
 #if defined(__CUDACC__)
 constexpr int O_END = O_END_DEV;
@@ -326,7 +334,7 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b) {
     V3 pf = cross(w, f0);
     for (int k = 0; k < T.nchild[b]; k++) {
         const int c = T.child[b][k];
-        const int o = O_IC + 21 * c;
+        const int o = O_IC + 21 * T.icslot[c];
         A.xx += F(o); A.xy += F(o + 1); A.xz += F(o + 2); A.yy += F(o + 3); A.yz += F(o + 4); A.zz += F(o + 5);
 #pragma unroll
         for (int i = 0; i < 9; i++) B.a[i] += F(o + 6 + i);
@@ -392,7 +400,7 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b) {
     for (int j = 0; j < 3; j++) setcol(RB, j, cross(r, col(Bp, j)));              // rx * Bp
 #pragma unroll
     for (int i = 0; i < 9; i++) Ap.a[i] = A1.a[i] - BtR.a[i] + RB.a[i];
-    const int o = O_IC + 21 * b;
+    const int o = O_IC + 21 * T.icslot[b];
     stS(S, o, upper(Ap)); stM(S, o + 6, Bp); stS(S, o + 15, upper(C1));
     const V3 fp = mul(Rj, paf);
     st3(S, O_PC + 6 * b, mul(Rj, pan) + cross(r, fp));
@@ -799,7 +807,7 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
                     F(O_VB + 3) += dv.x; F(O_VB + 4) += dv.y; F(O_VB + 5) += dv.z;
                 } else {
                     const V3 u = neg(pn);
-                    st3(S, O_TP + 3 * b, u);
+                    st3(S, O_UU + 3 * b, u);
                     const V3 Ku = mul(ldS(S, O_DI + 6 * b), u);
                     pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
                     pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
@@ -823,7 +831,7 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
                 const V3 alp = ld3(S, O_PC + 6 * p), ap = ld3(S, O_PC + 6 * p + 3);
                 const V3 aw = mulT(Rj, alp), al = mulT(Rj, ap + cross(alp, tv3(T.jorg, b)));
                 V3 u = mk(0, 0, 0);
-                if ((mask >> b) & 1) u = ld3(S, O_TP + 3 * b);
+                if ((mask >> b) & 1) u = ld3(S, O_UU + 3 * b);
                 const V3 qdd = mul(ldS(S, O_DI + 6 * b), u - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
                 st3(S, O_PC + 6 * b, aw + qdd);
                 st3(S, O_PC + 6 * b + 3, al);

@@ -32,6 +32,7 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
         T->parent[b] = p;
         T->depth[b] = b ? T->depth[p] + 1 : 0;
         if (b < T->level_start[T->depth[b]] || b >= T->level_start[T->depth[b] + 1]) SC_FAIL("body %d not in its level", b);
+        T->icslot[b] = (T->depth[b] & 1) * ICW + (b - T->level_start[T->depth[b]]);
         T->anc_mask[b] = (1 << b) | (b ? T->anc_mask[p] : 0);
         for (int d = 0; d < MAXLEV; d++) T->anc[b][d] = d < T->depth[b] ? T->anc[p][d] : (d == T->depth[b] ? b : -1);
         if (b) {
