@@ -13,6 +13,10 @@
 // (/root/reference/envs/humanoid_tracking_env.py:184-200, humanoid_stable_pd.py:124-135) as restated in
 // DESIGN.md §2; algorithms: articulated-body recursion specialised to spherical joints about the joint
 // centre (S=[1;0]), stable PD as an ABA with joint armature dt*Kd, contact-space Gauss-Seidel.
+// All spatial quantities are expressed in WORLD-ALIGNED axes about the owning body's origin (Pluecker transforms
+// between bodies are pure shifts by r = p_child - p_parent, no rotations): a spherical joint's motion subspace is
+// the whole angular 3-space in any basis and the armature dt*Kd is isotropic, so only the constant rigid-body
+// inertia has to be rotated into world axes, never the 6x6 articulated inertias.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -80,9 +84,12 @@ constexpr int O_VB = O_Q + 4 * NB;                // base world velocity: angula
 constexpr int O_W = O_VB + 6 - 3;                 // joint angular velocity in child frame (3, b>=1)
 constexpr int O_RW = O_W + 3 * NB;                // world rotation per body (9)
 constexpr int O_PW = O_RW + 9 * NB;               // world position of body origin (3)
-constexpr int O_TW = O_PW + 3 * NB;               // body twist in body coords: ang(3), lin(3)
-constexpr int O_TAU = O_TW + 6 * NB - 3;          // joint torque held over the sub-steps (3, b>=1)
-constexpr int O_UA = O_TAU + 3 * NB - 6;          // articulated inertia, angular block (sym 6, b>=1)
+constexpr int O_RJ = O_PW + 3 * NB - 3;           // r = p_b - p_parent in world axes (3, b>=1)
+constexpr int O_TW = O_RJ + 3 * NB;               // body twist, world axes: omega(3), velocity of the body origin(3)
+constexpr int O_WJ = O_TW + 6 * NB - 3;           // joint angular velocity in world axes, R_b * w (3, b>=1)
+constexpr int O_TAU = O_WJ + 3 * NB - 3;          // child-frame joint torque held over the sub-steps; during the
+                                                  // stable-PD solve: Kp*err - Kd*w (3, b>=1)
+constexpr int O_UA = O_TAU + 3 * NB - 6;          // articulated inertia (world axes), angular block (sym 6, b>=1)
 constexpr int O_UB = O_UA + 6 * NB - 9;           // articulated inertia, linear-from-angular block (9, b>=1)
 constexpr int O_DI = O_UB + 9 * NB - 6;           // (S^T IA S + armature)^-1 (sym 6, b>=1)
 constexpr int O_I0L = O_DI + 6 * NB;              // Cholesky factor of the base articulated inertia (21)
@@ -92,10 +99,9 @@ constexpr int O_IC = O_I0L + 21;                  // articulated-inertia contrib
                                                   // one slot per body of two adjacent tree levels (T.icslot)
 constexpr int O_PC = O_IC + 21 * 2 * ICW;         // bias-force contribution to the parent (6); later: accelerations
 constexpr int O_UU = O_PC + 6 * NB - 3;           // u = tau - S^T pA (3, b>=1); contact apply: -S^T pa
-constexpr int O_TP = O_UU + 3 * NB - 3;           // PD: Kp*err - Kd*w (3, b>=1)
-constexpr int O_SCR_END = O_TP + 3 * NB;
+constexpr int O_SCR_END = O_UU + 3 * NB;
 constexpr int O_CB = O_SCR_END;                   // contact body (int)
-constexpr int O_CR = O_CB + MAXC;                 // contact point relative to body origin, body coords (3)
+constexpr int O_CR = O_CB + MAXC;                 // contact point relative to the body origin, world axes (3)
 constexpr int O_CD = O_CR + 3 * MAXC;             // signed distance
 constexpr int O_NC = O_CD + MAXC;                 // number of contacts (int)
 constexpr int O_TM = O_NC + 1;                    // mask of bodies on a root path of some contact (int)
@@ -203,8 +209,13 @@ SC_DEV M3 quat2R(float x, float y, float z, float w) {
              2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
     return R;
 }
-// rotate a symmetric / general 3x3 block: R M R^T
-SC_DEV M3 rot(const M3 &R, const M3 &M) { return mulBt(mul(R, M), R); }
+// R A R^T for a symmetric A
+SC_DEV S3 rotS(const M3 &R, const S3 &A) {
+    const V3 m0 = mul(A, row(R, 0)), m1 = mul(A, row(R, 1)), m2 = mul(A, row(R, 2));   // columns of A R^T
+    S3 O = {dot(row(R, 0), m0), dot(row(R, 0), m1), dot(row(R, 0), m2), dot(row(R, 1), m1), dot(row(R, 1), m2),
+            dot(row(R, 2), m2)};
+    return O;
+}
 
 // ---- shared-memory load/store helpers ----------------------------------------------------------------------
 SC_DEV V3 ld3(const float *S, int o) { return mk(F(o), F(o + 1), F(o + 2)); }
@@ -284,22 +295,29 @@ SC_DEV int tile_max_int(const float *sm, int off) {
 // ============================================================================================================
 SC_DEV void fk_body(float *S, const Tables &T, int b, bool full) {
     if (b == 0) {
-        M3 R = ldRj(S, 0);
-        if (full) { stM(S, O_RW, R); st3(S, O_PW, ld3(S, O_P0)); }
-        st3(S, O_TW, mulT(R, ld3(S, O_VB)));
-        st3(S, O_TW + 3, mulT(R, ld3(S, O_VB + 3)));
+        if (full) { stM(S, O_RW, ldRj(S, 0)); st3(S, O_PW, ld3(S, O_P0)); }
+        st3(S, O_TW, ld3(S, O_VB));
+        st3(S, O_TW + 3, ld3(S, O_VB + 3));
     } else {
         const int p = T.parent[b];
-        M3 Rj = ldRj(S, b);
-        V3 r = tv3(T.jorg, b);
+        M3 R;
+        V3 r;
         if (full) {
-            M3 Rp = ldM(S, O_RW + 9 * p);
-            stM(S, O_RW + 9 * b, mul(Rp, Rj));
-            st3(S, O_PW + 3 * b, ld3(S, O_PW + 3 * p) + mul(Rp, r));
+            const M3 Rp = ldM(S, O_RW + 9 * p);
+            R = mul(Rp, ldRj(S, b));
+            r = mul(Rp, tv3(T.jorg, b));
+            stM(S, O_RW + 9 * b, R);
+            st3(S, O_RJ + 3 * b, r);
+            st3(S, O_PW + 3 * b, ld3(S, O_PW + 3 * p) + r);
+        } else {
+            R = ldM(S, O_RW + 9 * b);
+            r = ld3(S, O_RJ + 3 * b);
         }
-        V3 wp = ld3(S, O_TW + 6 * p), vp = ld3(S, O_TW + 6 * p + 3);
-        st3(S, O_TW + 6 * b, mulT(Rj, wp) + ld3(S, O_W + 3 * b));
-        st3(S, O_TW + 6 * b + 3, mulT(Rj, vp + cross(wp, r)));
+        const V3 wjw = mul(R, ld3(S, O_W + 3 * b));
+        const V3 wp = ld3(S, O_TW + 6 * p), vp = ld3(S, O_TW + 6 * p + 3);
+        st3(S, O_WJ + 3 * b, wjw);
+        st3(S, O_TW + 6 * b, wp + wjw);
+        st3(S, O_TW + 6 * b + 3, vp + cross(wp, r));
     }
 }
 
@@ -316,14 +334,17 @@ SC_DEV void fk_sweep(float *sm, const TT &T, int L0, int L1, bool full) {
 }
 
 // ============================================================================================================
-// articulated-body algorithm (PD = stable-PD variant: pd inertia set, armature dt*Kd, torque from O_TP)
+// articulated-body algorithm (PD = stable-PD variant: pd inertia set, armature dt*Kd, O_TAU holds Kp err - Kd w)
 // ============================================================================================================
 template <bool PD>
 SC_DEV void aba_backward_body(float *S, const Tables &T, int b) {
     const float *I = (PD ? T.ipd : T.idyn) + 10 * b;
     const float m = I[0];
-    const V3 hh = mk(I[1], I[2], I[3]);
-    S3 A = {I[4], I[5], I[6], I[7], I[8], I[9]};
+    const M3 R = ldM(S, O_RW + 9 * b);
+    // rigid-body inertia about the body origin, rotated into world axes
+    const V3 hh = mul(R, mk(I[1], I[2], I[3]));
+    const S3 Ab = {I[4], I[5], I[6], I[7], I[8], I[9]};
+    S3 A = rotS(R, Ab);
     M3 B = {{0, hh.z, -hh.y, -hh.z, 0, hh.x, hh.y, -hh.x, 0}};   // -skew(h)
     S3 C = {m, 0, 0, m, 0, m};
     const V3 w = ld3(S, O_TW + 6 * b), v = ld3(S, O_TW + 6 * b + 3);
@@ -356,21 +377,18 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b) {
 #pragma unroll
         for (int i = 0; i < 6; i++) F(O_PC + i) = x[i];
         if (!PD) {
-            // world-frame base velocity update: w += h R alpha ; v += h (R (a + w x v) + g)
-            M3 R = ldM(S, O_RW);
-            V3 al = mk(x[0], x[1], x[2]), a = mk(x[3], x[4], x[5]) + cross(w, v);
-            V3 dw = mul(R, al), dv = mul(R, a);
-            F(O_VB) += T.h * dw.x; F(O_VB + 1) += T.h * dw.y; F(O_VB + 2) += T.h * dw.z;
-            F(O_VB + 3) += T.h * (dv.x + T.g[0]); F(O_VB + 4) += T.h * (dv.y + T.g[1]); F(O_VB + 5) += T.h * (dv.z + T.g[2]);
+            // base velocity update: w += h alpha ; v += h (a + w x v + g)   (spatial -> classical acceleration)
+            const V3 a = mk(x[3], x[4], x[5]) + cross(w, v);
+            F(O_VB) += T.h * x[0]; F(O_VB + 1) += T.h * x[1]; F(O_VB + 2) += T.h * x[2];
+            F(O_VB + 3) += T.h * (a.x + T.g[0]); F(O_VB + 4) += T.h * (a.y + T.g[1]); F(O_VB + 5) += T.h * (a.z + T.g[2]);
         }
         return;
     }
     const float arm = PD ? T.dt * T.kd[b] : 0.0f;
     S3 D = A; D.xx += arm; D.yy += arm; D.zz += arm;
     const S3 K = inv(D);
-    const V3 tau = ld3(S, (PD ? O_TP : O_TAU) + 3 * b);
-    const V3 u = tau - pn;
-    const V3 wj = ld3(S, O_W + 3 * b);
+    const V3 u = mul(R, ld3(S, O_TAU + 3 * b)) - pn;      // child-frame torque (PD: Kp err - Kd w) in world axes
+    const V3 wj = ld3(S, O_WJ + 3 * b);
     const V3 cw = cross(w, wj), cv = cross(v, wj);
     stS(S, O_UA + 6 * b, A); stM(S, O_UB + 9 * b, B); stS(S, O_DI + 6 * b, K); st3(S, O_UU + 3 * b, u);
     const M3 Am = tom(A), Km = tom(K);
@@ -381,53 +399,50 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b) {
 #pragma unroll
     for (int i = 0; i < 9; i++) { Aa.a[i] = Am.a[i] - AKA.a[i]; Ba.a[i] = B.a[i] - BKA.a[i]; Ca.a[i] = Cm.a[i] - BKB.a[i]; }
     const V3 Ku = mul(K, u);
-    V3 pan = pn + mul(Aa, cw) + mulT(Ba, cv) + mul(A, Ku);
-    V3 paf = pf + mul(Ba, cw) + mul(Ca, cv) + mul(B, Ku);
-    // to parent coordinates: rotate by Rj, then shift the reference point by r
-    const M3 Rj = ldRj(S, b);
-    const V3 r = tv3(T.jorg, b);
-    const M3 A1 = rot(Rj, Aa), B1 = rot(Rj, Ba), C1 = rot(Rj, Ca);
+    const V3 pan = pn + mul(Aa, cw) + mulT(Ba, cv) + mul(A, Ku);
+    const V3 paf = pf + mul(Ba, cw) + mul(Ca, cv) + mul(B, Ku);
+    // shift the reference point to the parent's origin (r = p_b - p_parent); axes are shared, nothing to rotate
+    const V3 r = ld3(S, O_RJ + 3 * b);
     M3 CR, Bp, Ap;
 #pragma unroll
-    for (int i = 0; i < 3; i++) setrow(CR, i, cross(row(C1, i), r));              // C1 * rx
+    for (int i = 0; i < 3; i++) setrow(CR, i, cross(row(Ca, i), r));              // Ca * rx
 #pragma unroll
-    for (int i = 0; i < 9; i++) Bp.a[i] = B1.a[i] - CR.a[i];
-    // Ap = A1 - B1^T rx + rx B1 - rx C1 rx = A1 - B1^T rx + rx Bp
+    for (int i = 0; i < 9; i++) Bp.a[i] = Ba.a[i] - CR.a[i];
+    // Ap = Aa - Ba^T rx + rx Ba - rx Ca rx = Aa - Ba^T rx + rx Bp
     M3 BtR, RB;
 #pragma unroll
-    for (int i = 0; i < 3; i++) setrow(BtR, i, cross(col(B1, i), r));             // B1^T * rx
+    for (int i = 0; i < 3; i++) setrow(BtR, i, cross(col(Ba, i), r));             // Ba^T * rx
 #pragma unroll
     for (int j = 0; j < 3; j++) setcol(RB, j, cross(r, col(Bp, j)));              // rx * Bp
 #pragma unroll
-    for (int i = 0; i < 9; i++) Ap.a[i] = A1.a[i] - BtR.a[i] + RB.a[i];
+    for (int i = 0; i < 9; i++) Ap.a[i] = Aa.a[i] - BtR.a[i] + RB.a[i];
     const int o = O_IC + 21 * T.icslot[b];
-    stS(S, o, upper(Ap)); stM(S, o + 6, Bp); stS(S, o + 15, upper(C1));
-    const V3 fp = mul(Rj, paf);
-    st3(S, O_PC + 6 * b, mul(Rj, pan) + cross(r, fp));
-    st3(S, O_PC + 6 * b + 3, fp);
+    stS(S, o, upper(Ap)); stM(S, o + 6, Bp); stS(S, o + 15, upper(Ca));
+    st3(S, O_PC + 6 * b, pan + cross(r, paf));
+    st3(S, O_PC + 6 * b + 3, paf);
 }
 
 template <bool PD>
 SC_DEV void aba_forward_body(float *S, const Tables &T, int b) {
     const int p = T.parent[b];
-    const M3 Rj = ldRj(S, b);
-    const V3 r = tv3(T.jorg, b);
+    const V3 r = ld3(S, O_RJ + 3 * b);
     const V3 alp = ld3(S, O_PC + 6 * p), ap = ld3(S, O_PC + 6 * p + 3);
-    const V3 w = ld3(S, O_TW + 6 * b), v = ld3(S, O_TW + 6 * b + 3), wj = ld3(S, O_W + 3 * b);
-    const V3 aw = mulT(Rj, alp) + cross(w, wj);
-    const V3 al = mulT(Rj, ap + cross(alp, r)) + cross(v, wj);
+    const V3 w = ld3(S, O_TW + 6 * b), v = ld3(S, O_TW + 6 * b + 3), wj = ld3(S, O_WJ + 3 * b);
+    const V3 aw = alp + cross(w, wj);
+    const V3 al = ap + cross(alp, r) + cross(v, wj);
     const S3 A = ldS(S, O_UA + 6 * b), K = ldS(S, O_DI + 6 * b);
     const M3 B = ldM(S, O_UB + 9 * b);
     const V3 qdd = mul(K, ld3(S, O_UU + 3 * b) - mul(A, aw) - mulT(B, al));
     st3(S, O_PC + 6 * b, aw + qdd);
     st3(S, O_PC + 6 * b + 3, al);
+    const V3 qc = mulT(ldM(S, O_RW + 9 * b), qdd);        // joint acceleration in child-frame coordinates
     if (PD) {
         // tau = Kp err - Kd (w + dt qdd), clamped per axis (humanoid_stable_pd.py:52-59 max_forces)
         const float kd = T.dt * T.kd[b], mf = T.maxf[b];
-        V3 t = ld3(S, O_TP + 3 * b) - kd * qdd;
+        const V3 t = ld3(S, O_TAU + 3 * b) - kd * qc;
         st3(S, O_TAU + 3 * b, mk(fminf(mf, fmaxf(-mf, t.x)), fminf(mf, fmaxf(-mf, t.y)), fminf(mf, fmaxf(-mf, t.z))));
     } else {
-        st3(S, O_W + 3 * b, wj + T.h * qdd);
+        st3(S, O_W + 3 * b, ld3(S, O_W + 3 * b) + T.h * qc);
     }
 }
 
@@ -472,15 +487,15 @@ SC_DEV void pd_term_body(float *S, const Tables &T, int b, const float *act) {
     float s = sqrtf(dx * dx + dy * dy + dz * dz);
     float k = s > 1e-12f ? 2.0f * atan2f(s, dw) / s : 0.0f;
     const float kp = T.kp[b], kd = T.kd[b];
-    st3(S, O_TP + 3 * b, mk(kp * k * dx - kd * w.x, kp * k * dy - kd * w.y, kp * k * dz - kd * w.z));
+    st3(S, O_TAU + 3 * b, mk(kp * k * dx - kd * w.x, kp * k * dy - kd * w.y, kp * k * dz - kd * w.z));
 }
 
 // ============================================================================================================
 // ground contact
 // ============================================================================================================
-// unit direction k of the contact frame in the coordinates of a body with world rotation R:
-// n = +z, t1 = -y, t2 = +x (Bullet's btPlaneSpace1 of the plane normal)
-SC_DEV V3 cdir(const M3 &R, int k) { return k == 0 ? row(R, 2) : (k == 1 ? neg(row(R, 1)) : row(R, 0)); }
+// unit direction k of the ground-contact frame (world axes): n = +z, t1 = -y, t2 = +x (Bullet's btPlaneSpace1 of the
+// plane normal)
+SC_DEV V3 cdir(int k) { return k == 0 ? mk(0, 0, 1) : (k == 1 ? mk(0, -1, 0) : mk(1, 0, 0)); }
 SC_DEV float cproj(V3 w, int k) { return k == 0 ? w.z : (k == 1 ? -w.y : w.x); }
 
 // Candidate points (sphere centres with a radius, box corners with radius 0) against the plane z = 0.
@@ -493,9 +508,10 @@ SC_DEV void write_contact(float *S, const Tables &T, int j, int c, float z) {
     const int b = T.cand_body[c];
     const float *pt = T.cand + 4 * c;
     F(O_CB + j) = i2f(b);
-    F(O_CR + 3 * j) = pt[0] - pt[3] * F(O_RW + 9 * b + 6);
-    F(O_CR + 3 * j + 1) = pt[1] - pt[3] * F(O_RW + 9 * b + 7);
-    F(O_CR + 3 * j + 2) = pt[2] - pt[3] * F(O_RW + 9 * b + 8);
+    const V3 o = mul(ldM(S, O_RW + 9 * b), mk(pt[0], pt[1], pt[2]));      // lowest point of the sphere: centre - r ez
+    F(O_CR + 3 * j) = o.x;
+    F(O_CR + 3 * j + 1) = o.y;
+    F(O_CR + 3 * j + 2) = o.z - pt[3];
     F(O_CD + j) = z;
 }
 
@@ -574,7 +590,7 @@ SC_DEV void collide(float *sm, const TT &T, int L0, int L1 SC_PROF_ARGS) {
 SC_DEV void contact_column(float *S, const Tables &T, int nc, int c) {
     const int j = c / 3, k = c - 3 * j;
     const int bj = f2i(F(O_CB + j)), dj = T.depth[bj];
-    const V3 f = cdir(ldM(S, O_RW + 9 * bj), k);
+    const V3 f = cdir(k);
     V3 pn = neg(cross(ld3(S, O_CR + 3 * j), f)), pf = neg(f);
     V3 u[MAXLEV];
 #pragma unroll
@@ -586,10 +602,7 @@ SC_DEV void contact_column(float *S, const Tables &T, int nc, int c) {
             const V3 Ku = mul(ldS(S, O_DI + 6 * b), u[d]);
             pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
             pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
-            const M3 Rj = ldRj(S, b);
-            const V3 fp = mul(Rj, pf);
-            pn = mul(Rj, pn) + cross(tv3(T.jorg, b), fp);
-            pf = fp;
+            pn = pn + cross(ld3(S, O_RJ + 3 * b), pf);
         }
     }
     float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
@@ -608,15 +621,14 @@ SC_DEV void contact_column(float *S, const Tables &T, int nc, int c) {
             for (int d = 1; d < MAXLEV; d++) {
                 if (d <= di) {
                     const int b = T.anc[bi][d];
-                    const M3 Rj = ldRj(S, b);
-                    const V3 pw = mulT(Rj, aw), pl = mulT(Rj, al + cross(aw, tv3(T.jorg, b)));
+                    al = al + cross(aw, ld3(S, O_RJ + 3 * b));
                     const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);
-                    const V3 qdd = mul(ldS(S, O_DI + 6 * b), uu - mul(ldS(S, O_UA + 6 * b), pw) - mulT(ldM(S, O_UB + 9 * b), pl));
-                    aw = pw + qdd; al = pl;
+                    const V3 qdd = mul(ldS(S, O_DI + 6 * b), uu - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
+                    aw = aw + qdd;
                 }
             }
         }
-        const V3 a = mul(ldM(S, O_RW + 9 * bi), al + cross(aw, ld3(S, O_CR + 3 * i)));
+        const V3 a = al + cross(aw, ld3(S, O_CR + 3 * i));
 #pragma unroll
         for (int kk = 0; kk < 3; kk++) {
             const int rr = 3 * i + kk;
@@ -694,8 +706,7 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
         const int nc = f2i(F(O_NC));
         for (int j = slot; j < nc; j += QUAD) {
             const int b = f2i(F(O_CB + j));
-            const V3 rl = ld3(S, O_CR + 3 * j);
-            const V3 vp = mul(ldM(S, O_RW + 9 * b), ld3(S, O_TW + 6 * b + 3) + cross(ld3(S, O_TW + 6 * b), rl));
+            const V3 vp = ld3(S, O_TW + 6 * b + 3) + cross(ld3(S, O_TW + 6 * b), ld3(S, O_CR + 3 * j));
             const float dist = F(O_CD + j);
             F(O_RHS + 3 * j) = -vp.z - (dist > 0 ? dist / T.h : dist * T.erp / T.h);
             F(O_RHS + 3 * j + 1) = vp.y;
@@ -789,9 +800,8 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
                     const int c = T.child[b][k];
                     if ((mask >> c) & 1) { pn = pn + ld3(S, O_PC + 6 * c); pf = pf + ld3(S, O_PC + 6 * c + 3); }
                 }
-                const M3 R = ldM(S, O_RW + 9 * b);
                 for (int j = 0; j < nc; j++) if (f2i(F(O_CB + j)) == b) {
-                    const V3 f = F(O_LAM + 3 * j) * cdir(R, 0) + F(O_LAM + 3 * j + 1) * cdir(R, 1) + F(O_LAM + 3 * j + 2) * cdir(R, 2);
+                    const V3 f = mk(F(O_LAM + 3 * j + 2), -F(O_LAM + 3 * j + 1), F(O_LAM + 3 * j));   // sum_k lam_k cdir(k)
                     pn = pn - cross(ld3(S, O_CR + 3 * j), f);
                     pf = pf - f;
                 }
@@ -802,19 +812,16 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
                     solve6(L, x);
 #pragma unroll
                     for (int i = 0; i < 6; i++) F(O_PC + i) = x[i];
-                    const V3 dw = mul(R, mk(x[0], x[1], x[2])), dv = mul(R, mk(x[3], x[4], x[5]));
-                    F(O_VB) += dw.x; F(O_VB + 1) += dw.y; F(O_VB + 2) += dw.z;
-                    F(O_VB + 3) += dv.x; F(O_VB + 4) += dv.y; F(O_VB + 5) += dv.z;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) F(O_VB + i) += x[i];
                 } else {
                     const V3 u = neg(pn);
                     st3(S, O_UU + 3 * b, u);
                     const V3 Ku = mul(ldS(S, O_DI + 6 * b), u);
                     pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
                     pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
-                    const M3 Rj = ldRj(S, b);
-                    const V3 fp = mul(Rj, pf);
-                    st3(S, O_PC + 6 * b, mul(Rj, pn) + cross(tv3(T.jorg, b), fp));
-                    st3(S, O_PC + 6 * b + 3, fp);
+                    st3(S, O_PC + 6 * b, pn + cross(ld3(S, O_RJ + 3 * b), pf));
+                    st3(S, O_PC + 6 * b + 3, pf);
                 }
             }
         }
@@ -827,15 +834,13 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
             const int mask = f2i(F(O_TM)), nc = f2i(F(O_NC));
             if (b < T.level_start[d + 1] && nc > 0) {
                 const int p = T.parent[b];
-                const M3 Rj = ldRj(S, b);
-                const V3 alp = ld3(S, O_PC + 6 * p), ap = ld3(S, O_PC + 6 * p + 3);
-                const V3 aw = mulT(Rj, alp), al = mulT(Rj, ap + cross(alp, tv3(T.jorg, b)));
+                const V3 aw = ld3(S, O_PC + 6 * p), al = ld3(S, O_PC + 6 * p + 3) + cross(aw, ld3(S, O_RJ + 3 * b));
                 V3 u = mk(0, 0, 0);
                 if ((mask >> b) & 1) u = ld3(S, O_UU + 3 * b);
                 const V3 qdd = mul(ldS(S, O_DI + 6 * b), u - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
                 st3(S, O_PC + 6 * b, aw + qdd);
                 st3(S, O_PC + 6 * b + 3, al);
-                st3(S, O_W + 3 * b, ld3(S, O_W + 3 * b) + qdd);
+                st3(S, O_W + 3 * b, ld3(S, O_W + 3 * b) + mulT(ldM(S, O_RW + 9 * b), qdd));
             }
         }
         SC_SYNC();
@@ -933,10 +938,9 @@ SC_DEV void features(float *sm, const TT &T, int L0, int L1) {
             V3 cp = mk(0, 0, 0), cv = mk(0, 0, 0);
             for (int i = 0; i < T.ncp; i++) {
                 const int b = T.cp_body[i];
-                const V3 off = tv3(T.cp_off, i);
-                const M3 R = ldM(S, O_RW + 9 * b);
-                const V3 p = ld3(S, O_PW + 3 * b) + mul(R, off);
-                const V3 v = mul(R, ld3(S, O_TW + 6 * b + 3) + cross(ld3(S, O_TW + 6 * b), off));
+                const V3 off = mul(ldM(S, O_RW + 9 * b), tv3(T.cp_off, i));
+                const V3 p = ld3(S, O_PW + 3 * b) + off;
+                const V3 v = ld3(S, O_TW + 6 * b + 3) + cross(ld3(S, O_TW + 6 * b), off);
                 cp = cp + T.cp_mass[i] * p;
                 cv = cv + T.cp_mass[i] * v;
                 for (int e = 0; e < T.nee; e++) if (T.ee[e] == i) st3(S, O_FEAT + 6 + 3 * e, p);
