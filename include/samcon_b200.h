@@ -26,6 +26,8 @@ extern "C" {
 #define SC_MAX_CAND 96    /* ground-contact candidate points */
 #define SC_MAX_CPOINTS 24 /* cost points = URDF links */
 #define SC_MAX_CONTACTS 8 /* per-sample cap, deepest first */
+#define SC_MAX_PRIMS 24   /* self-collision primitives (sphere-swept segments) */
+#define SC_MAX_PAIRS 128  /* self-collision primitive pairs */
 
 #define SC_OK 0
 #define SC_EINVAL (-1)
@@ -57,6 +59,13 @@ typedef struct sc_model {
     float dt;                    /* 1/fps_sim */
     int32_t num_substeps, num_solver_iters, max_contacts;
     float gravity[3], friction, erp, contact_threshold, max_velocity;
+    /* link-vs-link contact (URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS,
+     * /root/reference/envs/humanoid_stable_pd.py:10-13); npair = 0 switches it off (cfg self_collision: False) */
+    int32_t nprim, npair;
+    const int32_t *prim_body;    /* [nprim] */
+    const float *prim;           /* [nprim,7] sphere-swept segment in the body frame: p0 xyz, p1 xyz, radius */
+    const int32_t *pair;         /* [npair,2] primitive indices; links neither equal nor ancestor-related */
+    float friction_self;         /* link lateral friction x link lateral friction */
 } sc_model;
 
 typedef struct sc_context *sc_handle;

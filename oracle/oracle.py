@@ -52,7 +52,7 @@ class Oracle:
         t = character.raw_tables()
         sp = character.sim
         simp = [sp.dt, sp.num_substeps, sp.num_solver_iters, *sp.gravity, sp.friction, sp.erp,
-                sp.contact_threshold, sp.max_contacts, sp.max_velocity]
+                sp.contact_threshold, sp.max_contacts, sp.max_velocity, float(bool(sp.self_collision)), sp.friction_self]
         keep = []
 
         def D(x):
@@ -150,6 +150,16 @@ class Oracle:
         out = np.zeros((256, 5))
         n = lib().oc_contacts(self._h, _d(state)[1], out.ctypes.data_as(C.POINTER(C.c_double)))
         return out[:n]
+
+    def contacts_full(self, state):
+        """rows: link, link2 (-1 = ground), point on link (3), point on link2 (3), normal link2->link (3), distance"""
+        out = np.zeros((256, 12))
+        n = lib().oc_contacts_full(self._h, _d(state)[1], out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out[:n]
+
+    @property
+    def num_pairs(self):
+        return lib().oc_num_pairs(self._h)
 
     def step_torque(self, state, tau, nsub_total):
         s, sp = _d(np.array(state, dtype=np.float64, copy=True))

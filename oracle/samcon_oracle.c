@@ -32,6 +32,7 @@
 #define MAXV 102
 #define MAXCAND 256
 #define MAXROW (3 * MAXCAND)
+#define MAXPAIR 512
 
 typedef struct {
     int nl, parent[MAXL], jtype[MAXL], dof[MAXL], nv, nj, jlink[MAXL];
@@ -42,6 +43,9 @@ typedef struct {
     double kp[MAXL], kd[MAXL], maxf[MAXL];
     double dt; int nsub, niter; double g[3], mu, erp, cthresh; int maxc; double maxvel;
     double jw[MAXL]; int nee, ee[8]; double cw[5], height;
+    /* self collision (URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS, humanoid_stable_pd.py:10-13) */
+    int selfcol, npair, pair_a[MAXPAIR], pair_b[MAXPAIR];
+    double mu_self, cap_p0[MAXS][3], cap_p1[MAXS][3], cap_r[MAXS];
 } oc_model;
 
 typedef struct {
@@ -158,11 +162,45 @@ static void spatial_inertia(double m, const double *c, const double *Ic, double 
     for (int i = 0; i < 3; i++) I6[6 * (3 + i) + 3 + i] = m;
 }
 
+/* Self-collision geometry.  Every collision primitive is stood in for by a sphere-swept segment (p0, p1, r) in its
+ * link frame: spheres and capsules exactly; a box by the capsule along its longest side with the same reach along
+ * that side and the same cross-section area (r = sqrt(s1 s2) / 2 for the two short sides) -- DESIGN.md §2 lists
+ * this as a deviation from Bullet's box-box / box-convex narrow phase.  Pairs: shapes of two different links that
+ * are not in an ancestor relation (EXCLUDE_ALL_PARENTS), in shape order. */
+static void self_collision_setup(oc_model *m) {
+    for (int s = 0; s < m->ns; s++) {
+        double e[3] = {0, 0, 0}, a[3], r;
+        if (m->sh_kind[s] == 0) r = m->sh_dims[s][0];
+        else if (m->sh_kind[s] == 1) { r = m->sh_dims[s][0]; e[2] = 0.5 * m->sh_dims[s][1]; }
+        else {
+            int k = 0;
+            for (int i = 1; i < 3; i++) if (m->sh_dims[s][i] > m->sh_dims[s][k]) k = i;
+            double prod = 1;
+            for (int i = 0; i < 3; i++) if (i != k) prod *= m->sh_dims[s][i];
+            r = 0.5 * sqrt(prod);
+            e[k] = 0.5 * m->sh_dims[s][k] - r;
+            if (e[k] < 0) e[k] = 0;
+        }
+        mv3(m->sh_rot[s], e, a);
+        for (int c = 0; c < 3; c++) { m->cap_p0[s][c] = m->sh_pos[s][c] + a[c]; m->cap_p1[s][c] = m->sh_pos[s][c] - a[c]; }
+        m->cap_r[s] = r;
+    }
+    m->npair = 0;
+    if (!m->selfcol) return;
+    for (int a = 0; a < m->ns; a++) for (int b = a + 1; b < m->ns; b++) {
+        int la = m->sh_link[a], lb = m->sh_link[b], rel = la == lb;
+        for (int p = m->parent[la]; p >= 0 && !rel; p = m->parent[p]) if (p == lb) rel = 1;
+        for (int p = m->parent[lb]; p >= 0 && !rel; p = m->parent[p]) if (p == la) rel = 1;
+        if (!rel && m->npair < MAXPAIR) { m->pair_a[m->npair] = a; m->pair_b[m->npair] = b; m->npair++; }
+    }
+}
+
 oc_model *oc_create(int nl, const int *parent, const int *jtype, const double *jorg, const double *com,
                     const double *mass, const double *com_dyn, const double *I_dyn, const double *com_pd,
                     const double *I_pd, int ns, const int *sh_link, const int *sh_kind, const double *sh_dims,
                     const double *sh_pos, const double *sh_rot, const double *kp, const double *kd,
-                    const double *maxf, const double *simp /* dt,nsub,niter,gx,gy,gz,mu,erp,cthresh,maxc,maxvel */,
+                    const double *maxf,
+                    const double *simp /* dt,nsub,niter,gx,gy,gz,mu,erp,cthresh,maxc,maxvel,selfcol,mu_self */,
                     const double *jw, int nee, const int *ee, const double *cw, double height) {
     if (nl > MAXL || ns > MAXS) return NULL;
     oc_model *m = (oc_model *)calloc(1, sizeof(oc_model));
@@ -190,6 +228,8 @@ oc_model *oc_create(int nl, const int *parent, const int *jtype, const double *j
     m->mu = simp[6]; m->erp = simp[7]; m->cthresh = simp[8]; m->maxc = (int)simp[9]; m->maxvel = simp[10];
     m->nee = nee; for (int k = 0; k < nee; k++) m->ee[k] = ee[k];
     memcpy(m->cw, cw, 40); m->height = height;
+    m->selfcol = (int)simp[11]; m->mu_self = simp[12];
+    self_collision_setup(m);
     return m;
 }
 void oc_destroy(oc_model *m) { free(m); }
@@ -391,10 +431,33 @@ static void stable_pd(const oc_model *m, const oc_state *st, const oc_kin *k, co
  * plane_implicit.urdf at z = 0 (/root/reference/envs/humanoid_tracking_env.py:75-76).  Stateless
  * manifold: sphere -> lowest point, capsule -> lowest point of each cap, box -> corners; a point joins
  * the solve when its height is below the contact threshold; deepest `maxc` kept (ties: lower index). */
-typedef struct { int link; double pos[3], dist; } oc_contact;
+typedef struct { int link, link2; double pos[3], pos2[3], n[3], dist, mu; } oc_contact;
+
+static double clamp01(double x) { return x < 0 ? 0 : (x > 1 ? 1 : x); }
+/* closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9); parallel segments: s = 0 */
+static void seg_seg(const double *p1, const double *q1, const double *p2, const double *q2, double *c1, double *c2) {
+    double d1[3], d2[3], r[3], s, t;
+    for (int k = 0; k < 3; k++) { d1[k] = q1[k] - p1[k]; d2[k] = q2[k] - p2[k]; r[k] = p1[k] - p2[k]; }
+    double a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r);
+    const double EPS = 1e-12;
+    if (a <= EPS && e <= EPS) s = t = 0;
+    else if (a <= EPS) { s = 0; t = clamp01(f / e); }
+    else {
+        double c = dot3(d1, r);
+        if (e <= EPS) { t = 0; s = clamp01(-c / a); }
+        else {
+            double b = dot3(d1, d2), den = a * e - b * b;
+            s = den > 1e-6 * a * e ? clamp01((b * f - c * e) / den) : 0;
+            t = (b * s + f) / e;
+            if (t < 0) { t = 0; s = clamp01(-c / a); }
+            else if (t > 1) { t = 1; s = clamp01((b - c) / a); }
+        }
+    }
+    for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
+}
 
 static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
-    oc_contact cand[MAXCAND];
+    static __thread oc_contact cand[MAXCAND];
     int n = 0;
     for (int s = 0; s < m->ns; s++) {
         int l = m->sh_link[s];
@@ -417,7 +480,30 @@ static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
             for (int a = 0; a < 3; a++) pw[a] += c[a];
             pw[2] -= r;
             if (pw[2] < m->cthresh && n < MAXCAND) {
-                cand[n].link = l; memcpy(cand[n].pos, pw, 24); cand[n].dist = pw[2]; n++;
+                oc_contact *cc = &cand[n++];
+                cc->link = l; cc->link2 = -1; memcpy(cc->pos, pw, 24); memcpy(cc->pos2, pw, 24);
+                cc->n[0] = 0; cc->n[1] = 0; cc->n[2] = 1; cc->dist = pw[2]; cc->mu = m->mu;
+            }
+        }
+    }
+    /* link vs link: one point per primitive pair, normal from the second link to the first */
+    for (int pi = 0; pi < m->npair; pi++) {
+        int sa = m->pair_a[pi], sb = m->pair_b[pi], la = m->sh_link[sa], lb = m->sh_link[sb];
+        double a0[3], a1[3], b0[3], b1[3], c1[3], c2[3], t[3], d[3];
+        mv3(k->R[la], m->cap_p0[sa], t); for (int a = 0; a < 3; a++) a0[a] = k->p[la][a] + t[a];
+        mv3(k->R[la], m->cap_p1[sa], t); for (int a = 0; a < 3; a++) a1[a] = k->p[la][a] + t[a];
+        mv3(k->R[lb], m->cap_p0[sb], t); for (int a = 0; a < 3; a++) b0[a] = k->p[lb][a] + t[a];
+        mv3(k->R[lb], m->cap_p1[sb], t); for (int a = 0; a < 3; a++) b1[a] = k->p[lb][a] + t[a];
+        seg_seg(a0, a1, b0, b1, c1, c2);
+        for (int a = 0; a < 3; a++) d[a] = c1[a] - c2[a];
+        double len = sqrt(dot3(d, d)), dist = len - m->cap_r[sa] - m->cap_r[sb];
+        if (dist < m->cthresh && len > 1e-9 && n < MAXCAND) {
+            oc_contact *cc = &cand[n++];
+            cc->link = la; cc->link2 = lb; cc->dist = dist; cc->mu = m->mu_self;
+            for (int a = 0; a < 3; a++) {
+                cc->n[a] = d[a] / len;
+                cc->pos[a] = c1[a] - m->cap_r[sa] * cc->n[a];
+                cc->pos2[a] = c2[a] + m->cap_r[sb] * cc->n[a];
             }
         }
     }
@@ -435,18 +521,36 @@ static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
 }
 
 /* row of the contact Jacobian: d . v_point = J . v_gen */
-static void contact_row(const oc_model *m, const oc_kin *k, const oc_contact *c, const double *d, double *J) {
-    memset(J, 0, sizeof(double) * m->nv);
-    for (int a = c->link; a >= 0; a = m->parent[a]) {
+static void point_row_acc(const oc_model *m, const oc_kin *k, int link, const double *pos, const double *d, double sgn,
+                          double *J) {
+    for (int a = link; a >= 0; a = m->parent[a]) {
         if (m->dof[a] < 0) continue;
         double rel[3], rxd[3];
-        for (int e = 0; e < 3; e++) rel[e] = c->pos[e] - k->p[a][e];
+        for (int e = 0; e < 3; e++) rel[e] = pos[e] - k->p[a][e];
         cross(rel, d, rxd);
         for (int e = 0; e < 3; e++) {
             double ax[3] = {k->R[a][e], k->R[a][3 + e], k->R[a][6 + e]};
-            J[m->dof[a] + e] = dot3(ax, rxd);
-            if (a == 0) J[3 + e] = dot3(ax, d);
+            J[m->dof[a] + e] += sgn * dot3(ax, rxd);
+            if (a == 0) J[3 + e] += sgn * dot3(ax, d);
         }
+    }
+}
+/* d . (v_point(link) - v_point2(link2)) = J . v_gen; link2 < 0 is the fixed ground */
+static void contact_row(const oc_model *m, const oc_kin *k, const oc_contact *c, const double *d, double *J) {
+    memset(J, 0, sizeof(double) * m->nv);
+    point_row_acc(m, k, c->link, c->pos, d, 1.0, J);
+    if (c->link2 >= 0) point_row_acc(m, k, c->link2, c->pos2, d, -1.0, J);
+}
+/* Bullet's btPlaneSpace1: two unit tangents p, q for a unit normal n */
+static void plane_space(const double *n, double *p, double *q) {
+    if (fabs(n[2]) > 0.7071067811865475244008443621048490) {
+        double a = n[1] * n[1] + n[2] * n[2], k = 1.0 / sqrt(a);
+        p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+        q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+    } else {
+        double a = n[0] * n[0] + n[1] * n[1], k = 1.0 / sqrt(a);
+        p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+        q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
     }
 }
 
@@ -475,10 +579,11 @@ static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const doub
     for (int i = 0; i < nv; i++) v[i] += h * qdd[i];
 
     if (nc > 0) {
-        static const double dirs[3][3] = {{0, 0, 1}, {0, -1, 0}, {1, 0, 0}}; /* n, btPlaneSpace1(n) */
-        int nr = 3 * nc;
         for (int c = 0; c < nc; c++) for (int d = 0; d < 3; d++) {
             int r = 3 * c + d;
+            double dirs[3][3]; /* n, btPlaneSpace1(n): (0,0,1) -> (0,-1,0), (1,0,0) */
+            memcpy(dirs[0], con[c].n, 24);
+            plane_space(con[c].n, dirs[1], dirs[2]);
             contact_row(m, k, &con[c], dirs[d], J[r]);
             chol_solve(M, nv, J[r], MinvJt[r]);
             double dg = 0, rel = 0;
@@ -498,7 +603,7 @@ static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const doub
                     for (int i = 0; i < nv; i++) jv += J[r][i] * dv[i];
                     double nl = lam[r] + b[r] - jv / diag[r];
                     double lo = 0, hi = 1e30;
-                    if (d) { hi = m->mu * lam[3 * c]; lo = -hi; }
+                    if (d) { hi = con[c].mu * lam[3 * c]; lo = -hi; }
                     if (nl < lo) nl = lo;
                     if (nl > hi) nl = hi;
                     double dl = nl - lam[r];
@@ -673,6 +778,18 @@ int oc_contacts(const oc_model *m, const double *state, double *out /* [maxc,5]:
     }
     return n;
 }
+int oc_contacts_full(const oc_model *m, const double *state, double *out /* [maxc,12]: link,link2,pos,pos2,n,dist */) {
+    oc_state st; oc_kin k; oc_contact con[MAXCAND];
+    unpack(m, state, &st); fk(m, &st, &k);
+    int n = collide(m, &k, con);
+    for (int i = 0; i < n; i++) {
+        double *o = out + 12 * i;
+        o[0] = con[i].link; o[1] = con[i].link2; memcpy(o + 2, con[i].pos, 24); memcpy(o + 5, con[i].pos2, 24);
+        memcpy(o + 8, con[i].n, 24); o[11] = con[i].dist;
+    }
+    return n;
+}
+int oc_num_pairs(const oc_model *m) { return m->npair; }
 /* free dynamics with given generalised forces and no stable PD: used by conservation tests */
 void oc_step_torque(const oc_model *m, double *state, const double *tau, int nsub_total) {
     oc_state st; oc_kin k;

@@ -33,6 +33,8 @@ class ScModel(C.Structure):
         ("num_substeps", C.c_int32), ("num_solver_iters", C.c_int32), ("max_contacts", C.c_int32),
         ("gravity", C.c_float * 3), ("friction", C.c_float), ("erp", C.c_float), ("contact_threshold", C.c_float),
         ("max_velocity", C.c_float),
+        ("nprim", C.c_int32), ("npair", C.c_int32), ("prim_body", i32p), ("prim", f32p), ("pair", i32p),
+        ("friction_self", C.c_float),
     ]
 
 
@@ -66,6 +68,11 @@ def make_model(character):
     m.num_substeps, m.num_solver_iters, m.max_contacts = sp.num_substeps, sp.num_solver_iters, sp.max_contacts
     m.gravity = (C.c_float * 3)(*[float(x) for x in sp.gravity])
     m.friction, m.erp, m.contact_threshold, m.max_velocity = sp.friction, sp.erp, sp.contact_threshold, sp.max_velocity
+    m.nprim = len(t["prim_body"])
+    m.npair = len(t["pair"]) if sp.self_collision else 0
+    m.prim_body, m.prim = I(t["prim_body"]), F(t["prim"])
+    m.pair = I(t["pair"] if len(t["pair"]) else np.zeros((1, 2)))
+    m.friction_self = sp.friction_self
     return m, keep
 
 

@@ -14,7 +14,7 @@ using namespace sc;
 constexpr int TABLE_WORDS = (sizeof(Tables) + 15) / 16 * 4;
 
 template <int WPB>
-__global__ void __launch_bounds__(32 * WPB) sc_rollout_kernel(const Tables *__restrict__ gT, RolloutArgs a) {
+__global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *__restrict__ gT, RolloutArgs a) {
     extern __shared__ __align__(16) float smem[];
     {
         const int4 *src = reinterpret_cast<const int4 *>(gT);

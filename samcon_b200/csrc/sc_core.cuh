@@ -60,6 +60,16 @@ constexpr int TILE = 4;   // samples per warp
 constexpr int QUAD = 8;   // lanes per sample (the name predates the 8-lane mapping)
 static_assert(TILE * QUAD == 32, "one tile per warp");
 
+// self-collision tables (part of Tables, in shared memory)
+constexpr int NPRIM = SC_MAX_PRIMS, NPAIR = SC_MAX_PAIRS;
+constexpr int PAIRS_PER_LANE_MAX = (NPAIR + QUAD - 1) / QUAD, PRIMS_PER_LANE_MAX = (NPRIM + QUAD - 1) / QUAD;
+struct SelfTables {
+    int nprim, npair, prims_per_lane, pairs_per_lane;
+    float prim[NPRIM * 8];              // sphere-swept segment in the body frame: p0, p1, radius, bounding radius about the midpoint
+    float pair_r2[NPAIR];               // (bounding radius a + bounding radius b + contact threshold)^2
+    unsigned char pair_a[NPAIR], pair_b[NPAIR], prim_body[NPRIM];
+};
+
 // ---- derived model tables (copied to shared memory once per CTA) ------------------------------------------
 struct Tables {
     int nb, nlev, ncand, ncp, nee, niter, nsub, maxc, nj;
@@ -70,8 +80,10 @@ struct Tables {
     int cand_body[SC_MAX_CAND], cp_body[SC_MAX_CPOINTS], ee[4];
     float jorg[NB * 3], idyn[NB * 10], ipd[NB * 10], kp[NB], kd[NB], maxf[NB], cand[SC_MAX_CAND * 4];
     float cp_off[SC_MAX_CPOINTS * 3], cp_mass[SC_MAX_CPOINTS], jw[NB], cw[5];
-    float height, dt, h, g[3], mu, erp, cthresh, maxvel, inv_total_mass;
+    float height, dt, h, g[3], mu, mu_self, erp, cthresh, maxvel, inv_total_mass;
+    SelfTables self;
 };
+
 
 // ---- per-sample shared-memory layout (32-bit words) --------------------------------------------------------
 // Regions marked (b>=1) have no slot for the root: their offset is pulled back by one stride so that
@@ -100,7 +112,7 @@ constexpr int O_IC = O_I0L + 21;                  // articulated-inertia contrib
 constexpr int O_PC = O_IC + 21 * 2 * ICW;         // bias-force contribution to the parent (6); later: accelerations
 constexpr int O_UU = O_PC + 6 * NB - 3;           // u = tau - S^T pA (3, b>=1); contact apply: -S^T pa
 constexpr int O_SCR_END = O_UU + 3 * NB;
-constexpr int O_CB = O_SCR_END;                   // contact body (int)
+constexpr int O_CB = O_SCR_END;                   // contact bodies (int): body a | (body b + 1) << 8, b = -1: the ground
 constexpr int O_CR = O_CB + MAXC;                 // contact point relative to the body origin, world axes (3)
 constexpr int O_CD = O_CR + 3 * MAXC;             // signed distance
 constexpr int O_NC = O_CD + MAXC;                 // number of contacts (int)
@@ -109,11 +121,19 @@ constexpr int O_RHS = O_TM + 1;
 constexpr int O_LAM = O_RHS + NR;
 constexpr int O_END_DEV = O_LAM + NR;
 constexpr int O_AM = O_IC;                        // contact-space matrix, packed lower triangle (contact solve)
-constexpr int O_ZC = O_IC;                        // collide: candidate heights ...
-constexpr int O_CNT = O_ZC + SC_MAX_CAND;         // ... and hits per lane
+constexpr int O_ZC = O_IC;                        // collide: signed distance per candidate (ground points, then pairs) ...
+constexpr int O_CNT = O_ZC + SC_MAX_CAND + NPAIR; // ... hits per lane (ground, pairs) ...
+constexpr int O_PCEN = O_CNT + 2 * QUAD;          // ... and world centres of the self-collision primitives (3)
+constexpr int HL_MAX = 32;                        // hits (distance, candidate) compacted over O_PCEN when more than maxc
+constexpr int O_HL = O_PCEN;
+static_assert(2 * HL_MAX <= 3 * NPRIM, "hit list must fit in PCEN");
+// second body of a contact: live from collide to the end of the contact solve, while O_WJ is dead
+constexpr int O_CR2 = O_WJ + 3;                   // contact point relative to body b's origin, world axes (3)
+constexpr int O_CN = O_CR2 + 3 * MAXC;            // contact normal, from body b (or the ground) to body a (3)
 constexpr int O_FEAT = O_RHS;                     // end of window: com(3) comvel(3) ee(4x3)
 static_assert(NR * (NR + 1) / 2 <= O_SCR_END - O_IC, "AM must fit in the scratch block");
-static_assert(SC_MAX_CAND + QUAD <= 21 * 2 * ICW, "ZC + CNT must fit in IC");
+static_assert(O_PCEN + 3 * NPRIM <= O_SCR_END, "collide scratch must fit in the scratch block");
+static_assert(O_CN + 3 * MAXC <= O_WJ + 3 * NB, "second-body contact data must fit in WJ");
 static_assert(18 <= 2 * NR, "FEAT must fit in RHS + LAM");
 #if defined(__CUDACC__)
 constexpr int O_END = O_END_DEV;
@@ -315,7 +335,7 @@ SC_DEV void fk_body(float *S, const Tables &T, int b, bool full) {
         }
         const V3 wjw = mul(R, ld3(S, O_W + 3 * b));
         const V3 wp = ld3(S, O_TW + 6 * p), vp = ld3(S, O_TW + 6 * p + 3);
-        st3(S, O_WJ + 3 * b, wjw);
+        if (full) st3(S, O_WJ + 3 * b, wjw);      // the velocity-only pass runs while O_WJ holds contact data
         st3(S, O_TW + 6 * b, wp + wjw);
         st3(S, O_TW + 6 * b + 3, vp + cross(wp, r));
     }
@@ -493,30 +513,108 @@ SC_DEV void pd_term_body(float *S, const Tables &T, int b, const float *act) {
 // ============================================================================================================
 // ground contact
 // ============================================================================================================
-// unit direction k of the ground-contact frame (world axes): n = +z, t1 = -y, t2 = +x (Bullet's btPlaneSpace1 of the
-// plane normal)
-SC_DEV V3 cdir(int k) { return k == 0 ? mk(0, 0, 1) : (k == 1 ? mk(0, -1, 0) : mk(1, 0, 0)); }
-SC_DEV float cproj(V3 w, int k) { return k == 0 ? w.z : (k == 1 ? -w.y : w.x); }
+// contact frame of a unit normal n: d[0] = n, d[1], d[2] = Bullet's btPlaneSpace1(n); the ground's n = +z gives
+// t1 = -y, t2 = +x
+struct Frame { V3 d[3]; };
+SC_DEV Frame contact_frame(V3 n) {
+    Frame fr;
+    fr.d[0] = n;
+    if (fabsf(n.z) > 0.70710678f) {
+        const float a = n.y * n.y + n.z * n.z, k = 1.0f / sqrtf(a);
+        fr.d[1] = mk(0, -n.z * k, n.y * k);
+        fr.d[2] = mk(a * k, -n.x * fr.d[1].z, n.x * fr.d[1].y);
+    } else {
+        const float a = n.x * n.x + n.y * n.y, k = 1.0f / sqrtf(a);
+        fr.d[1] = mk(-n.y * k, n.x * k, 0);
+        fr.d[2] = mk(-n.z * fr.d[1].y, n.z * fr.d[1].x, a * k);
+    }
+    return fr;
+}
+// frame of contact j: ground contacts (no second body) have the constant frame +z, -y, +x
+SC_DEV Frame contact_frame_of(const float *S, int j, int cb) {
+    if ((cb >> 8) == 0) { Frame fr; fr.d[0] = mk(0, 0, 1); fr.d[1] = mk(0, -1, 0); fr.d[2] = mk(1, 0, 0); return fr; }
+    return contact_frame(ld3(S, O_CN + 3 * j));
+}
+SC_DEV int cb_a(int cb) { return cb & 255; }
+SC_DEV int cb_b(int cb) { return (cb >> 8) - 1; }
 
 // Candidate points (sphere centres with a radius, box corners with radius 0) against the plane z = 0.
-// Stage 1: the lanes of a sample test contiguous chunks of the candidate list and count their hits.
-// Stage 2: with the counts of the lower lanes as offset every lane appends its hits, so the contact list is in
-// candidate order; only when more than `maxc` points are inside the margin does lane 0 pick the deepest serially.
+// Stage 1: the lanes of a sample test contiguous chunks of the ground candidates and place the self-collision
+// primitives' centres.  Stage 2: broad phase over the primitive pairs (bounding spheres), narrow phase for the few
+// that pass.  Stage 3: with the hit counts of the lower lanes as offset every lane appends its hits, so the contact
+// list is in candidate order (ground points, then pairs); only when more than `maxc` candidates are inside the
+// margin does lane 0 pick the deepest serially.
 constexpr int CAND_PER_LANE_MAX = (SC_MAX_CAND + QUAD - 1) / QUAD;
+constexpr float NO_HIT = 1.0e30f;
 
-SC_DEV void write_contact(float *S, const Tables &T, int j, int c, float z) {
-    const int b = T.cand_body[c];
-    const float *pt = T.cand + 4 * c;
-    F(O_CB + j) = i2f(b);
-    const V3 o = mul(ldM(S, O_RW + 9 * b), mk(pt[0], pt[1], pt[2]));      // lowest point of the sphere: centre - r ez
-    F(O_CR + 3 * j) = o.x;
-    F(O_CR + 3 * j + 1) = o.y;
-    F(O_CR + 3 * j + 2) = o.z - pt[3];
+SC_DEV float clamp01(float x) { return fminf(1.0f, fmaxf(0.0f, x)); }
+// closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9); parallel segments: s = 0
+SC_DEV void seg_seg(V3 p1, V3 q1, V3 p2, V3 q2, V3 &c1, V3 &c2) {
+    const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+    const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+    const float EPS = 1e-12f;
+    float s, t;
+    if (a <= EPS && e <= EPS) { s = 0; t = 0; }
+    else if (a <= EPS) { s = 0; t = clamp01(f / e); }
+    else {
+        const float c = dot(d1, r);
+        if (e <= EPS) { t = 0; s = clamp01(-c / a); }
+        else {
+            const float b = dot(d1, d2), den = a * e - b * b;
+            s = den > 1e-6f * a * e ? clamp01((b * f - c * e) / den) : 0.0f;
+            t = (b * s + f) / e;
+            if (t < 0) { t = 0; s = clamp01(-c / a); }
+            else if (t > 1) { t = 1; s = clamp01((b - c) / a); }
+        }
+    }
+    c1 = p1 + s * d1; c2 = p2 + t * d2;
+}
+SC_DEV V3 prim_point(const float *S, const SelfTables &ST, int p, int which) {
+    const int b = ST.prim_body[p];
+    const float *q = ST.prim + 8 * p + 3 * which;
+    return ld3(S, O_PW + 3 * b) + mul(ldM(S, O_RW + 9 * b), mk(q[0], q[1], q[2]));
+}
+// narrow phase of one primitive pair: surface points (world), unit normal from b to a, signed distance
+SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, V3 &pa, V3 &pb, V3 &n, float &dist) {
+    const int a = ST.pair_a[pr], b = ST.pair_b[pr];
+    V3 c1, c2;
+    seg_seg(prim_point(S, ST, a, 0), prim_point(S, ST, a, 1), prim_point(S, ST, b, 0), prim_point(S, ST, b, 1), c1, c2);
+    const V3 d = c1 - c2;
+    const float len2 = dot(d, d);
+    if (!(len2 > 1e-18f)) return false;
+    const float len = sqrtf(len2), ra = ST.prim[8 * a + 6], rb = ST.prim[8 * b + 6];
+    n = (1.0f / len) * d;
+    dist = len - ra - rb;
+    pa = c1 - ra * n; pb = c2 + rb * n;
+    return true;
+}
+
+// u = unified candidate index: ground point u < ncand, else primitive pair u - ncand
+SC_DEV void write_contact(float *S, const Tables &T, const SelfTables &ST, int j, int u, float z) {
+    if (u < T.ncand) {
+        const int b = T.cand_body[u];
+        const float *pt = T.cand + 4 * u;
+        F(O_CB + j) = i2f(b);
+        const V3 o = mul(ldM(S, O_RW + 9 * b), mk(pt[0], pt[1], pt[2]));      // lowest point of the sphere: centre - r ez
+        F(O_CR + 3 * j) = o.x;
+        F(O_CR + 3 * j + 1) = o.y;
+        F(O_CR + 3 * j + 2) = o.z - pt[3];
+    } else {
+        const int pr = u - T.ncand;
+        const int ba = ST.prim_body[ST.pair_a[pr]], bb = ST.prim_body[ST.pair_b[pr]];
+        V3 pa, pb, n;
+        float d;
+        pair_contact(S, ST, pr, pa, pb, n, d);
+        F(O_CB + j) = i2f(ba | ((bb + 1) << 8));
+        st3(S, O_CR + 3 * j, pa - ld3(S, O_PW + 3 * ba));
+        st3(S, O_CR2 + 3 * j, pb - ld3(S, O_PW + 3 * bb));
+        st3(S, O_CN + 3 * j, n);
+    }
     F(O_CD + j) = z;
 }
 
 template <class TT>
-SC_DEV void collide(float *sm, const TT &T, int L0, int L1 SC_PROF_ARGS) {
+SC_DEV void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int L1 SC_PROF_ARGS) {
     SC_STAGE {
         SC_LANE;
         const int c0 = slot * T.cand_per_lane;
@@ -534,36 +632,114 @@ SC_DEV void collide(float *sm, const TT &T, int L0, int L1 SC_PROF_ARGS) {
             }
         }
         F(O_CNT + slot) = i2f(hits);
+        if (ST.npair > 0)
+#pragma unroll
+            for (int i = 0; i < PRIMS_PER_LANE_MAX; i++) {
+                const int p = slot * ST.prims_per_lane + i;
+                if (i < ST.prims_per_lane && p < ST.nprim) {
+                    const int b = ST.prim_body[p];
+                    const float *q = ST.prim + 8 * p;
+                    const V3 mid = mk(0.5f * (q[0] + q[3]), 0.5f * (q[1] + q[4]), 0.5f * (q[2] + q[5]));
+                    st3(S, O_PCEN + 3 * p, ld3(S, O_PW + 3 * b) + mul(ldM(S, O_RW + 9 * b), mid));
+                }
+            }
     }
     SC_SYNC();
     SC_STAGE {
         SC_LANE;
-        int ofs = 0, total = 0;
+        // broad phase: bounding spheres of the primitives; the rare survivors go through the narrow phase afterwards
+        int hits = 0;
+        unsigned near = 0;
+#pragma unroll
+        for (int i = 0; i < PAIRS_PER_LANE_MAX; i++) {
+            const int pr = slot * ST.pairs_per_lane + i;
+            if (i < ST.pairs_per_lane && pr < ST.npair) {
+                const V3 d = ld3(S, O_PCEN + 3 * ST.pair_a[pr]) - ld3(S, O_PCEN + 3 * ST.pair_b[pr]);
+                near |= (dot(d, d) < ST.pair_r2[pr] ? 1u : 0u) << i;
+                F(O_ZC + T.ncand + pr) = NO_HIT;
+            }
+        }
+        while (near) {
+#if defined(__CUDA_ARCH__)
+            const int i = __ffs(near) - 1;
+#else
+            const int i = __builtin_ctz(near);
+#endif
+            near &= near - 1;
+            const int pr = slot * ST.pairs_per_lane + i;
+            V3 pa, pb, n;
+            float dist;
+            if (pair_contact(S, ST, pr, pa, pb, n, dist)) {
+                F(O_ZC + T.ncand + pr) = dist;
+                hits += dist < T.cthresh ? 1 : 0;
+            }
+        }
+        F(O_CNT + QUAD + slot) = i2f(hits);
+    }
+    SC_SYNC();
+    SC_STAGE {
+        SC_LANE;
+        int ofs = 0, ofs2 = 0, total = 0;
 #pragma unroll
         for (int l = 0; l < QUAD; l++) {
-            const int n = f2i(F(O_CNT + l));
+            const int n = f2i(F(O_CNT + l)), n2 = f2i(F(O_CNT + QUAD + l));
             ofs += l < slot ? n : 0;
-            total += n;
+            ofs2 += (l < slot ? n2 : 0) + n;
+            total += n + n2;
         }
 #if defined(SC_PROFILE) && defined(__CUDACC__)
         if (total > T.maxc) sc_prof_acc[23]++;
         sc_prof_acc[24] += total < T.maxc ? total : T.maxc;
 #endif
-        if (total <= T.maxc) {
-            const int c0 = slot * T.cand_per_lane;
+        const bool list = total > T.maxc && total <= HL_MAX;   // too many: compact (z, u) first, pick in parallel below
+        if (total <= T.maxc || list) {
             if (f2i(F(O_CNT + slot)) > 0)
                 for (int i = 0; i < T.cand_per_lane; i++) {
-                    const int c = c0 + i;
+                    const int c = slot * T.cand_per_lane + i;
                     if (c < T.ncand) {
                         const float z = F(O_ZC + c);
-                        if (z < T.cthresh) write_contact(S, T, ofs++, c, z);
+                        if (z < T.cthresh) {
+                            if (list) { F(O_HL + 2 * ofs) = z; F(O_HL + 2 * ofs + 1) = i2f(c); ofs++; }
+                            else write_contact(S, T, ST, ofs++, c, z);
+                        }
                     }
                 }
-            if (slot == 0) F(O_NC) = i2f(total);
-        } else if (slot == 0) {
-            // O_CB holds candidate indices and O_CD heights while the deepest maxc are being chosen
+            if (f2i(F(O_CNT + QUAD + slot)) > 0)
+                for (int i = 0; i < ST.pairs_per_lane; i++) {
+                    const int pr = slot * ST.pairs_per_lane + i;
+                    if (pr < ST.npair) {
+                        const float z = F(O_ZC + T.ncand + pr);
+                        if (z < T.cthresh) {
+                            if (list) { F(O_HL + 2 * ofs2) = z; F(O_HL + 2 * ofs2 + 1) = i2f(T.ncand + pr); ofs2++; }
+                            else write_contact(S, T, ST, ofs2++, T.ncand + pr, z);
+                        }
+                    }
+                }
+        }
+        if (slot == 0) F(O_NC) = i2f(total);
+    }
+    SC_SYNC();
+    if (tile_max_int(sm, O_NC) <= T.maxc) return;
+    // ---- more than maxc candidates inside the margin somewhere in the tile: keep the maxc deepest (ties: lower index),
+    // in candidate order.  Rank every hit against the compacted list; lists longer than HL_MAX fall back to lane 0.
+    SC_STAGE {
+        SC_LANE;
+        const int total = f2i(F(O_NC));
+        unsigned keep = 0;
+        if (total > T.maxc && total <= HL_MAX) {
+            for (int h = slot; h < total; h += QUAD) {
+                const float zh = F(O_HL + 2 * h);
+                int rank = 0;
+                for (int g = 0; g < total; g++) {
+                    const float zg = F(O_HL + 2 * g);
+                    rank += (zg < zh || (zg == zh && g < h)) ? 1 : 0;
+                }
+                keep |= (rank < T.maxc ? 1u : 0u) << h;
+            }
+        } else if (total > HL_MAX && slot == 0) {
+            // O_CB holds candidate indices and O_CD distances while the deepest maxc are being chosen
             int n = 0;
-            for (int c = 0; c < T.ncand; c++) {
+            for (int c = 0; c < T.ncand + ST.npair; c++) {
                 const float z = F(O_ZC + c);
                 if (!(z < T.cthresh)) continue;
                 if (n < T.maxc) { F(O_CB + n) = i2f(c); F(O_CD + n) = z; n++; continue; }
@@ -575,9 +751,30 @@ SC_DEV void collide(float *sm, const TT &T, int L0, int L1 SC_PROF_ARGS) {
                     F(O_CB + n - 1) = i2f(c); F(O_CD + n - 1) = z;
                 }
             }
-            for (int j = 0; j < n; j++) write_contact(S, T, j, f2i(F(O_CB + j)), F(O_CD + j));
-            F(O_NC) = i2f(n);
+            for (int j = 0; j < n; j++) write_contact(S, T, ST, j, f2i(F(O_CB + j)), F(O_CD + j));
         }
+        F(O_CNT + slot) = i2f((int)keep);
+        if (slot == 0) F(O_CNT + QUAD) = i2f(total);      // O_NC is rewritten in the next stage while others still need the count
+    }
+    SC_SYNC();
+    SC_STAGE {
+        SC_LANE;
+        const int total = f2i(F(O_CNT + QUAD));
+        if (total > T.maxc && total <= HL_MAX) {
+            unsigned keep = 0;
+#pragma unroll
+            for (int l = 0; l < QUAD; l++) keep |= (unsigned)f2i(F(O_CNT + l));
+            for (int h = slot; h < total; h += QUAD)
+                if ((keep >> h) & 1u) {
+#if defined(__CUDA_ARCH__)
+                    const int pos = __popc(keep & ((1u << h) - 1u));
+#else
+                    const int pos = __builtin_popcount(keep & ((1u << h) - 1u));
+#endif
+                    write_contact(S, T, ST, pos, f2i(F(O_HL + 2 * h + 1)), F(O_HL + 2 * h));
+                }
+        }
+        if (slot == 0 && total > T.maxc) F(O_NC) = i2f(T.maxc);
     }
     SC_SYNC();
 }
@@ -586,53 +783,74 @@ SC_DEV void collide(float *sm, const TT &T, int L0, int L1 SC_PROF_ARGS) {
 // the articulated system (inertias left in shared memory by the dynamics ABA) to a unit impulse along direction k
 // of contact j.  The impulse walks up the tree to the root (recording u = -S^T p per level in registers), the 6x6
 // base block is solved with the Cholesky factor kept from the ABA, and accelerations walk back down to the bodies
-// of the contacts i >= j; rows >= the column index land in the packed lower triangle O_AM.
+// of the contacts i >= j; rows >= the column index land in the packed lower triangle O_AM.  A link-vs-link contact
+// is the superposition of two such single-body problems (+f on body a, -f on body b): the second pass adds.
 SC_DEV void contact_column(float *S, const Tables &T, int nc, int c) {
     const int j = c / 3, k = c - 3 * j;
-    const int bj = f2i(F(O_CB + j)), dj = T.depth[bj];
-    const V3 f = cdir(k);
-    V3 pn = neg(cross(ld3(S, O_CR + 3 * j), f)), pf = neg(f);
-    V3 u[MAXLEV];
+    const int cbj = f2i(F(O_CB + j));
+    const V3 f0 = contact_frame_of(S, j, cbj).d[k];
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+        const int bj = side ? cb_b(cbj) : cb_a(cbj);
+        if (bj < 0) break;
+        const int dj = T.depth[bj];
+        const V3 f = side ? neg(f0) : f0;
+        V3 pn = neg(cross(ld3(S, (side ? O_CR2 : O_CR) + 3 * j), f)), pf = neg(f);
+        V3 u[MAXLEV];
 #pragma unroll
-    for (int d = MAXLEV - 1; d >= 1; d--) {
-        u[d] = mk(0, 0, 0);
-        if (d <= dj) {
-            const int b = T.anc[bj][d];
-            u[d] = neg(pn);
-            const V3 Ku = mul(ldS(S, O_DI + 6 * b), u[d]);
-            pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
-            pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
-            pn = pn + cross(ld3(S, O_RJ + 3 * b), pf);
-        }
-    }
-    float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
-#pragma unroll
-    for (int i = 0; i < 21; i++) L[i] = F(O_I0L + i);
-    solve6(L, x);
-    int bprev = -1;
-    V3 aw = mk(0, 0, 0), al = mk(0, 0, 0);
-    for (int i = j; i < nc; i++) {
-        const int bi = f2i(F(O_CB + i));
-        if (bi != bprev) {
-            bprev = bi;
-            const int di = T.depth[bi];
-            aw = mk(x[0], x[1], x[2]); al = mk(x[3], x[4], x[5]);
-#pragma unroll
-            for (int d = 1; d < MAXLEV; d++) {
-                if (d <= di) {
-                    const int b = T.anc[bi][d];
-                    al = al + cross(aw, ld3(S, O_RJ + 3 * b));
-                    const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);
-                    const V3 qdd = mul(ldS(S, O_DI + 6 * b), uu - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
-                    aw = aw + qdd;
-                }
+        for (int d = MAXLEV - 1; d >= 1; d--) {
+            u[d] = mk(0, 0, 0);
+            if (d <= dj) {
+                const int b = T.anc[bj][d];
+                u[d] = neg(pn);
+                const V3 Ku = mul(ldS(S, O_DI + 6 * b), u[d]);
+                pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
+                pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
+                pn = pn + cross(ld3(S, O_RJ + 3 * b), pf);
             }
         }
-        const V3 a = al + cross(aw, ld3(S, O_CR + 3 * i));
+        float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
 #pragma unroll
-        for (int kk = 0; kk < 3; kk++) {
-            const int rr = 3 * i + kk;
-            if (rr >= c) F(O_AM + rr * (rr + 1) / 2 + c) = cproj(a, kk);
+        for (int i = 0; i < 21; i++) L[i] = F(O_I0L + i);
+        solve6(L, x);
+        int bprev = -1;
+        V3 awc = mk(0, 0, 0), alc = mk(0, 0, 0);
+        for (int i = j; i < nc; i++) {
+            const int cbi = f2i(F(O_CB + i));
+            V3 a = mk(0, 0, 0);
+#pragma unroll 1
+            for (int s2 = 0; s2 < 2; s2++) {
+                const int bi = s2 ? cb_b(cbi) : cb_a(cbi);
+                if (bi < 0) break;
+                V3 aw = awc, al = alc;
+                if (s2 || bi != bprev) {
+                    const int di = T.depth[bi];
+                    aw = mk(x[0], x[1], x[2]); al = mk(x[3], x[4], x[5]);
+#pragma unroll
+                    for (int d = 1; d < MAXLEV; d++) {
+                        if (d <= di) {
+                            const int b = T.anc[bi][d];
+                            al = al + cross(aw, ld3(S, O_RJ + 3 * b));
+                            const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);
+                            const V3 qdd = mul(ldS(S, O_DI + 6 * b), uu - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
+                            aw = aw + qdd;
+                        }
+                    }
+                    if (!s2) { bprev = bi; awc = aw; alc = al; }
+                }
+                const V3 ap = al + cross(aw, ld3(S, (s2 ? O_CR2 : O_CR) + 3 * i));
+                a = s2 ? a - ap : ap;
+            }
+            const Frame fi = contact_frame_of(S, i, cbi);
+#pragma unroll
+            for (int kk = 0; kk < 3; kk++) {
+                const int rr = 3 * i + kk;
+                if (rr >= c) {
+                    const float v = dot(fi.d[kk], a);
+                    const int o = O_AM + rr * (rr + 1) / 2 + c;
+                    if (side) F(o) += v; else F(o) = v;
+                }
+            }
         }
     }
 }
@@ -650,7 +868,7 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
     const int slot = lane / TILE;
     const int nr = 3 * f2i(F(O_NC));
     constexpr int NRT = 3 * NCT, RPL = (NRT + QUAD - 1) / QUAD;     // rows per lane
-    float a[RPL][NRT], res[RPL], lam[RPL], dgi[RPL], lamn[NCT];
+    float a[RPL][NRT], res[RPL], lam[RPL], dgi[RPL], lamn[NCT], muc[NCT];
 #pragma unroll
     for (int m = 0; m < RPL; m++) {
         const int row = slot + QUAD * m;
@@ -665,8 +883,7 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
         lam[m] = 0.0f;
     }
 #pragma unroll
-    for (int c = 0; c < NCT; c++) lamn[c] = 0.0f;
-    const float mu = T.mu;
+    for (int c = 0; c < NCT; c++) { lamn[c] = 0.0f; muc[c] = (f2i(F(O_CB + c)) >> 8) ? T.mu_self : T.mu; }
     const int src0 = lane & (TILE - 1);
     for (int it = 0; it < T.niter; it++) {
 #pragma unroll
@@ -678,7 +895,7 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
                     constexpr int dummy = 0; (void)dummy;
                     const int r = 3 * c + k, owner = r % QUAD, m = r / QUAD;
                     float nl = lam[m] + res[m] * dgi[m];
-                    const float lim = k == 0 ? 3.0e38f : mu * lamn[c];
+                    const float lim = k == 0 ? 3.0e38f : muc[c] * lamn[c];
                     nl = fminf(lim, fmaxf(k == 0 ? 0.0f : -lim, nl));
                     float d = slot == owner ? nl - lam[m] : 0.0f;
                     if (slot == owner) lam[m] = nl;
@@ -705,17 +922,22 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
         SC_LANE;
         const int nc = f2i(F(O_NC));
         for (int j = slot; j < nc; j += QUAD) {
-            const int b = f2i(F(O_CB + j));
-            const V3 vp = ld3(S, O_TW + 6 * b + 3) + cross(ld3(S, O_TW + 6 * b), ld3(S, O_CR + 3 * j));
+            const int cb = f2i(F(O_CB + j)), ba = cb_a(cb), bb = cb_b(cb);
+            V3 vp = ld3(S, O_TW + 6 * ba + 3) + cross(ld3(S, O_TW + 6 * ba), ld3(S, O_CR + 3 * j));
+            if (bb >= 0) vp = vp - ld3(S, O_TW + 6 * bb + 3) - cross(ld3(S, O_TW + 6 * bb), ld3(S, O_CR2 + 3 * j));
+            const Frame fr = contact_frame_of(S, j, cb);
             const float dist = F(O_CD + j);
-            F(O_RHS + 3 * j) = -vp.z - (dist > 0 ? dist / T.h : dist * T.erp / T.h);
-            F(O_RHS + 3 * j + 1) = vp.y;
-            F(O_RHS + 3 * j + 2) = -vp.x;
+            F(O_RHS + 3 * j) = -dot(fr.d[0], vp) - (dist > 0 ? dist / T.h : dist * T.erp / T.h);
+            F(O_RHS + 3 * j + 1) = -dot(fr.d[1], vp);
+            F(O_RHS + 3 * j + 2) = -dot(fr.d[2], vp);
             F(O_LAM + 3 * j) = 0; F(O_LAM + 3 * j + 1) = 0; F(O_LAM + 3 * j + 2) = 0;
         }
         if (slot == QUAD - 1) {
             int mask = 0;
-            for (int j = 0; j < nc; j++) mask |= T.anc_mask[f2i(F(O_CB + j))];
+            for (int j = 0; j < nc; j++) {
+                const int cb = f2i(F(O_CB + j));
+                mask |= T.anc_mask[cb_a(cb)] | (cb_b(cb) >= 0 ? T.anc_mask[cb_b(cb)] : 0);
+            }
             F(O_TM) = i2f(mask);
         }
 #if !defined(__CUDACC__)
@@ -778,7 +1000,7 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
                         const float lam = F(O_LAM + r);
                         float nl = lam + F(O_RES + r) * F(O_DGI + r);
                         if (k == 0) nl = fmaxf(nl, 0.0f);
-                        else { const float lim = T.mu * F(O_LAM + 3 * c); nl = fminf(lim, fmaxf(-lim, nl)); }
+                        else { const float lim = ((f2i(F(O_CB + c)) >> 8) ? T.mu_self : T.mu) * F(O_LAM + 3 * c); nl = fminf(lim, fmaxf(-lim, nl)); }
                         F(O_LAM + r) = nl;
                         F(O_DEL + (t & 1)) = nl - lam;
                     }
@@ -800,10 +1022,15 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
                     const int c = T.child[b][k];
                     if ((mask >> c) & 1) { pn = pn + ld3(S, O_PC + 6 * c); pf = pf + ld3(S, O_PC + 6 * c + 3); }
                 }
-                for (int j = 0; j < nc; j++) if (f2i(F(O_CB + j)) == b) {
-                    const V3 f = mk(F(O_LAM + 3 * j + 2), -F(O_LAM + 3 * j + 1), F(O_LAM + 3 * j));   // sum_k lam_k cdir(k)
-                    pn = pn - cross(ld3(S, O_CR + 3 * j), f);
-                    pf = pf - f;
+                for (int j = 0; j < nc; j++) {
+                    const int cb = f2i(F(O_CB + j));
+                    const bool ona = cb_a(cb) == b, onb = cb_b(cb) == b;
+                    if (ona || onb) {
+                        const Frame fr = contact_frame_of(S, j, cb);
+                        const V3 f = F(O_LAM + 3 * j) * fr.d[0] + F(O_LAM + 3 * j + 1) * fr.d[1] + F(O_LAM + 3 * j + 2) * fr.d[2];
+                        if (ona) { pn = pn - cross(ld3(S, O_CR + 3 * j), f); pf = pf - f; }
+                        else { pn = pn + cross(ld3(S, O_CR2 + 3 * j), f); pf = pf + f; }
+                    }
                 }
                 if (b == 0) {
                     float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
@@ -1045,12 +1272,13 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             SC_CTA_SYNC();
             SC_T(13);
             if (sub) { fk_sweep(sm, T, L0, L1, true); SC_T(1); }
-            collide(sm, T, L0, L1 SC_PROF_PASS);
-            SC_T(4);
             aba<false>(sm, T, L0, L1);
             SC_T(5);
             SC_CTA_SYNC();
             SC_T(13);
+            // positions are those of the start of the sub-step; the ABA's scratch is free for the collision pass now
+            collide(sm, T, T.self, L0, L1 SC_PROF_PASS);
+            SC_T(4);
             const int ncmax = tile_max_int(sm, O_NC);
 #if defined(SC_PROFILE) && defined(__CUDACC__)
             sc_prof_acc[16]++; sc_prof_acc[17] += ncmax > 0; sc_prof_acc[18 + (ncmax + 1) / 2]++;

@@ -1,6 +1,7 @@
 // sc_tables.h -- host: derive the kernel's lookup tables (sc::Tables) from the C-ABI model description.
 #pragma once
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
 #include "sc_core.cuh"
 
@@ -9,6 +10,7 @@ namespace sc {
 inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) {
 #define SC_FAIL(...) do { snprintf(err, errlen, __VA_ARGS__); return SC_EINVAL; } while (0)
     memset(T, 0, sizeof(*T));
+    SelfTables *ST = &T->self;
     if (!m) SC_FAIL("null model");
     if (m->nb < 1 || m->nb > NB) SC_FAIL("nb=%d outside 1..%d", m->nb, NB);
     if (m->nlev < 1 || m->nlev > MAXLEV) SC_FAIL("nlev=%d outside 1..%d", m->nlev, MAXLEV);
@@ -65,8 +67,31 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
     for (int k = 0; k < 5; k++) T->cw[k] = m->cost_weights[k];
     T->height = m->height; T->dt = m->dt; T->h = m->dt / m->num_substeps;
     for (int k = 0; k < 3; k++) T->g[k] = m->gravity[k];
-    T->mu = m->friction; T->erp = m->erp; T->cthresh = m->contact_threshold; T->maxvel = m->max_velocity;
+    T->mu = m->friction; T->mu_self = m->friction_self; T->erp = m->erp; T->cthresh = m->contact_threshold; T->maxvel = m->max_velocity;
     T->inv_total_mass = (float)(1.0 / tm);
+    // self collision: primitives with bounding spheres, pairs with their broad-phase radius
+    if (m->npair < 0 || m->npair > NPAIR) SC_FAIL("npair=%d outside 0..%d", m->npair, NPAIR);
+    if (m->npair > 0) {
+        if (m->nprim < 1 || m->nprim > NPRIM || !m->prim || !m->prim_body || !m->pair) SC_FAIL("nprim=%d outside 1..%d", m->nprim, NPRIM);
+        ST->nprim = m->nprim; ST->npair = m->npair;
+        ST->prims_per_lane = (m->nprim + QUAD - 1) / QUAD;
+        ST->pairs_per_lane = (m->npair + QUAD - 1) / QUAD;
+        for (int p = 0; p < m->nprim; p++) {
+            if (m->prim_body[p] < 0 || m->prim_body[p] >= m->nb) SC_FAIL("bad prim_body");
+            ST->prim_body[p] = (unsigned char)m->prim_body[p];
+            const float *q = m->prim + 7 * p;
+            for (int k = 0; k < 7; k++) ST->prim[8 * p + k] = q[k];
+            const double dx = q[3] - q[0], dy = q[4] - q[1], dz = q[5] - q[2];
+            ST->prim[8 * p + 7] = (float)(q[6] + 0.5 * sqrt(dx * dx + dy * dy + dz * dz));
+        }
+        for (int i = 0; i < m->npair; i++) {
+            const int a = m->pair[2 * i], b = m->pair[2 * i + 1];
+            if (a < 0 || b < 0 || a >= m->nprim || b >= m->nprim) SC_FAIL("bad pair %d", i);
+            ST->pair_a[i] = (unsigned char)a; ST->pair_b[i] = (unsigned char)b;
+            const double r = (double)ST->prim[8 * a + 7] + ST->prim[8 * b + 7] + m->contact_threshold;
+            ST->pair_r2[i] = (float)(r * r * 1.0001);
+        }
+    }
     return SC_OK;
 #undef SC_FAIL
 }

@@ -40,6 +40,8 @@ class SimParams:
     contact_threshold: float = 0.02   # contactBreakingThreshold: points closer than this join the solve
     max_contacts: int = 8             # deepest-first cap per sample (device working-set bound)
     max_velocity: float = 100.0       # btMultiBody max coordinate velocity clamp
+    self_collision: bool = True       # URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS (humanoid_stable_pd.py:10-13)
+    friction_self: float = 0.8 * 0.8  # link lateral 0.8 x link lateral 0.8 (product rule)
 
 
 def _skew(v):
@@ -71,6 +73,46 @@ def _solid_inertia(s, mass):
     iax = 0.5 * mc * r * r + 0.4 * ms * r * r
     ipe = mc * (L * L / 12.0 + r * r / 4.0) + ms * (0.4 * r * r + 0.25 * L * L + 0.375 * L * r)
     return np.array([ipe, ipe, iax])
+
+
+def shape_capsule(s):
+    """Self-collision stand-in of a collision primitive: a sphere-swept segment (p0, p1, radius) in the shape's link
+    frame.  Spheres and capsules are exact.  A box becomes the capsule along its longest side with the same reach
+    along that side and the same cross-section area (r = half the geometric mean of the two short sides): the
+    link-vs-link narrow phase then is one closed-form segment-segment distance for every pair."""
+    if s.kind == SPHERE:
+        return s.pos.copy(), s.pos.copy(), float(s.dims[0])
+    if s.kind == CAPSULE:
+        a = s.rot @ np.array([0.0, 0.0, 0.5 * s.dims[1]])
+        return s.pos + a, s.pos - a, float(s.dims[0])
+    k = int(np.argmax(s.dims))
+    short = [s.dims[i] for i in range(3) if i != k]
+    r = 0.5 * float(np.sqrt(short[0] * short[1]))
+    e = np.zeros(3)
+    e[k] = max(0.0, 0.5 * s.dims[k] - r)
+    a = s.rot @ e
+    return s.pos + a, s.pos - a, r
+
+
+def self_collision_pairs(links):
+    """Shape pairs (i, j), i < j in URDF shape order, whose links are different and not in an ancestor relation
+    (URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS, humanoid_stable_pd.py:10-13)."""
+    anc = []
+    for i, l in enumerate(links):
+        a = set()
+        p = l.parent
+        while p >= 0:
+            a.add(p)
+            p = links[p].parent
+        anc.append(a)
+    sh_link = [i for i, l in enumerate(links) for _ in l.shapes]
+    pairs = []
+    for a in range(len(sh_link)):
+        for b in range(a + 1, len(sh_link)):
+            la, lb = sh_link[a], sh_link[b]
+            if la != lb and la not in anc[lb] and lb not in anc[la]:
+                pairs.append((a, b))
+    return pairs
 
 
 def link_inertia(link: Link, mode: str):
@@ -244,7 +286,17 @@ class Character:
                 for p in pts:
                     cand.append((b, *(off[i] + s.pos + s.rot @ p), r))
         cand = np.array(cand, dtype=np.float64)
+        # self-collision primitives (one per URDF shape, in shape order) in the frame of the moving body that carries
+        # the shape's link, and the primitive pairs that may touch
+        prim_body, prim = [], []
+        for i, l in enumerate(L):
+            for s in l.shapes:
+                p0, p1, r = shape_capsule(s)
+                prim_body.append(body_of_link[owner[i]])
+                prim.append([*(off[i] + p0), *(off[i] + p1), r])
+        pair = np.array(self_collision_pairs(L), dtype=np.int32).reshape(-1, 2)
         return {
+            "prim_body": np.array(prim_body, dtype=np.int32), "prim": np.array(prim, dtype=np.float64), "pair": pair,
             "nb": nb, "nlev": nlev, "level_start": np.array(level_start, dtype=np.int32),
             "parent": parent, "jidx": jidx, "jorg": jorg, "kp": kp, "kd": kd, "maxf": maxf,
             "inertia_dyn": inert["dyn"], "inertia_pd": inert["pd"],

@@ -59,3 +59,17 @@ def joint_rms(a, b):
     d = np.abs((qa * qb).sum(-1)) / (np.linalg.norm(qa, axis=-1) * np.linalg.norm(qb, axis=-1))
     ang = 2 * np.arccos(np.clip(d, 0, 1))
     return np.sqrt((ang ** 2).mean(-1))
+
+
+def qz(a):
+    return np.array([0.0, 0.0, np.sin(0.5 * a), np.cos(0.5 * a)])
+
+
+def legs_crossed(rng, inward=0.2, z=1.5, vel=0.0):
+    """Upright humanoid whose hips are rotated `inward` rad towards each other (thighs / shins / feet touch or
+    interpenetrate from ~0.1 rad on): the seeded source of link-vs-link contacts for the self-collision tests."""
+    s = stand(rng, 0.0, vel, z)
+    s[0:2] = 0
+    s[7:11] = qz(-inward)              # lhip (joint 0)
+    s[7 + 12:11 + 12] = qz(inward)     # rhip (joint 3)
+    return s

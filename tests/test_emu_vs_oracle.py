@@ -86,3 +86,60 @@ def test_parent_mapping_and_sequences(emu, character, oracle):
         os_, oc, _ = oracle.window(parents[pidx[k]][None], actions[k][None], targets[seq[k]], 10)
         assert joint_rms(st[k][None], os_).max() < 1e-4
         np.testing.assert_allclose(cost[k], oc[0], rtol=1e-3)
+
+
+def test_self_contact_window(emu, character, oracle):
+    """Link-vs-link contacts (thighs / shins / feet squeezed together by the PD targets, airborne and standing):
+    two-body contact rows, per-contact friction, general contact frames."""
+    from helpers import legs_crossed
+    rng = np.random.default_rng(7)
+    parents = np.array([legs_crossed(rng, 0.03 + 0.01 * i, 2.0 if i % 2 else 0.995, 0.1) for i in range(8)])
+    actions = np.array([legs_crossed(rng, 0.3 + 0.02 * i)[7:75] for i in range(8)])
+    target = stand(rng)
+    n_self = sum((oracle.contacts_full(oracle.step(p, a, 60))[:, 1] >= 0).sum() for p, a in zip(parents, actions))
+    assert n_self >= 6                                              # the scenario really produces link-link contacts
+    st, cost, info = _window(emu, character, parents, actions, target, 100)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
+    assert joint_rms(st, ost).max() < 1e-3
+    np.testing.assert_allclose(st[:, :3], ost[:, :3], atol=2e-4)
+    np.testing.assert_allclose(cost, ocost, rtol=1e-3)
+
+
+def test_self_collision_switch(emu, walk_cfg):
+    """cfg self_collision: False (npair = 0) must reproduce the oracle built without pairs."""
+    from helpers import legs_crossed
+    from oracle.oracle import Oracle
+    from samcon_b200.model import Character, SimParams
+    ch = Character.from_config(walk_cfg, SimParams(self_collision=False))
+    o = Oracle(ch)
+    rng = np.random.default_rng(8)
+    parents = np.array([legs_crossed(rng, 0.05, 2.0, 0.1) for _ in range(4)])
+    actions = np.array([legs_crossed(rng, 0.35)[7:75] for _ in range(4)])
+    target = stand(rng)
+    st, cost, _ = _window(emu, ch, parents, actions, target, 300)
+    ost, ocost, _ = o.window(parents, actions, target, 300)
+    assert joint_rms(st, ost).max() < 1e-4
+    assert (2 * np.arccos(np.abs(st[:, 10]))).min() > 0.3          # the legs passed through each other
+
+
+def test_contact_cap_paths(emu, character, oracle):
+    """More candidates inside the margin than max_contacts: the parallel pick (<= 32 hits: both feet flat plus
+    link-vs-link hits) and the serial fallback (a humanoid lying on the ground: > 32 hits) must keep the same
+    deepest-8 set as the oracle."""
+    from helpers import legs_crossed
+    rng = np.random.default_rng(9)
+    flat = []
+    for i in range(3):                                              # lying on the back / side, a few cm above ground
+        s = stand(rng, 0.02, 0.1, 0.09 + 0.01 * i)
+        s[3:7] = [0, 0, 0, 1] if i < 2 else [0, np.sin(0.4), 0, np.cos(0.4)]
+        flat.append(s)
+    feet = [legs_crossed(rng, 0.12 + 0.02 * i, 0.97, 0.05) for i in range(3)]   # feet 1 cm into the ground, shins touching
+    parents = np.array(flat + feet)
+    counts = [len(oracle.contacts_full(p)) for p in parents]
+    assert counts == [character.sim.max_contacts] * 6
+    actions = np.array([near_action(p, rng, 0.05) for p in parents])
+    target = stand(rng)
+    st, cost, _ = _window(emu, character, parents, actions, target, 6)
+    ost, ocost, _ = oracle.window(parents, actions, target, 6)
+    assert joint_rms(st, ost).max() < 2e-4
+    np.testing.assert_allclose(st[:, :3], ost[:, :3], atol=1e-4)

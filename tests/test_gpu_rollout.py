@@ -124,3 +124,22 @@ def test_ragged_sizes(pool, oracle):
         ost, ocost, _ = oracle.window(parents[pidx], actions, target, 10)
         assert joint_rms(st.cpu().numpy(), ost).max() < JOINT_TOL
         np.testing.assert_allclose(cost.cpu().numpy(), ocost, rtol=COST_RTOL)
+
+
+def test_self_contact_window(pool, oracle):
+    """Link-vs-link contact rows on the GPU: legs squeezed together by the PD targets, airborne and standing."""
+    from helpers import legs_crossed
+    rng = np.random.default_rng(7)
+    n = 24
+    parents = np.array([legs_crossed(rng, 0.03 + 0.004 * i, 2.0 if i % 2 else 0.995, 0.1) for i in range(n)])
+    actions = np.array([legs_crossed(rng, 0.3 + 0.008 * i)[7:75] for i in range(n)])
+    target = stand(rng)
+    n_self = sum((oracle.contacts_full(oracle.step(p, a, 60))[:, 1] >= 0).sum() for p, a in zip(parents[:8], actions[:8]))
+    assert n_self >= 6
+    st, cost, info = _run(pool, parents, actions, target, 100, 1)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
+    rms = joint_rms(st, ost)
+    print(f"self-contact joint rms: median {np.median(rms):.2e} max {rms.max():.2e}")
+    assert rms.max() < JOINT_TOL
+    np.testing.assert_allclose(st[:, :3], ost[:, :3], atol=2e-4)
+    np.testing.assert_allclose(cost, ocost, rtol=COST_RTOL)

@@ -128,3 +128,68 @@ def test_cost_terms_against_numpy(oracle, character, walk_cfg):
 def test_topk_ties_by_index(oracle):
     c = np.array([3.0, 1.0, 2.0, 1.0, 5.0, 1.0])
     assert list(oracle.topk(c, 4)) == [1, 3, 5, 2]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# link-vs-link contact (self_collision: True, walk.yml:113; flags humanoid_stable_pd.py:10-13)
+# ---------------------------------------------------------------------------------------------------------------
+def test_self_collision_pairs_exclude_ancestors(oracle, character):
+    from samcon_b200.model import self_collision_pairs
+    pairs = self_collision_pairs(character.links)
+    assert oracle.num_pairs == len(pairs) == 125
+    sh_link = [i for i, l in enumerate(character.links) for _ in l.shapes]
+    names = [character.links[i].name for i in sh_link]
+    pn = {frozenset((names[a], names[b])) for a, b in pairs}
+    has = lambda a, b: frozenset((a, b)) in pn
+    assert has("lknee", "rknee") and has("lankle", "rankle") and has("lelbow", "rhip") and has("lwrist", "rwrist")
+    assert not any("root" in p for p in pn)                       # the root is everybody's ancestor
+    assert not has("lhip", "lknee") and not has("chest", "lelbow") and not has("lelbow", "lwrist")
+
+
+def test_self_contact_geometry(oracle, character):
+    from helpers import legs_crossed
+    rng = np.random.default_rng(0)
+    assert len(oracle.contacts_full(legs_crossed(rng, 0.0))) == 0          # rest pose: nothing within 2 cm
+    c = oracle.contacts_full(legs_crossed(rng, 0.12))
+    assert len(c) >= 1 and (c[:, 1] >= 0).all()
+    for r in c:
+        n, pa, pb, d = r[8:11], r[2:5], r[5:8], r[11]
+        assert abs(np.linalg.norm(n) - 1) < 1e-12
+        assert np.allclose(pa - pb, d * n, atol=1e-12)             # the two surface points are d apart along the normal
+        assert d < character.sim.contact_threshold
+    names = {(character.links[int(r[0])].name, character.links[int(r[1])].name) for r in c}
+    assert ("lknee", "rknee") in names
+
+
+def test_self_contact_conserves_momentum_and_separates(walk_cfg):
+    """No gravity, airborne, PD squeezing the legs together: contact impulses are internal, so linear momentum stays
+    at the integrator's own (first-order, see test_momentum_error_is_first_order_in_dt) drift level; the legs must
+    rest against each other instead of passing through to the PD target."""
+    from helpers import legs_crossed
+    from oracle.oracle import Oracle
+    from samcon_b200.model import Character, SimParams
+    res = {}
+    for sc in (True, False):
+        ch = Character.from_config(walk_cfg, SimParams(gravity=(0.0, 0.0, 0.0), self_collision=sc))
+        o = Oracle(ch)
+        rng = np.random.default_rng(1)
+        s = legs_crossed(rng, 0.05, 2.0)
+        target = legs_crossed(rng, 0.35, 2.0)[7:75]
+        m = np.array([l.mass for l in ch.links])
+
+        def momentum(s):
+            pos, vel, c, cv = o.link_coms(s)
+            return m.sum() * cv
+
+        p0 = momentum(s)
+        deepest = 0.0
+        for _ in range(30):
+            s = o.step(s, target, 10)
+            c = o.contacts_full(s)
+            if len(c):
+                deepest = min(deepest, c[:, 11].min())
+        res[sc] = (np.abs(momentum(s) - p0).max(), deepest, s)
+    assert res[True][0] < 5e-4 and res[True][0] < 2 * res[False][0] + 1e-5
+    assert res[True][1] > -0.01            # with self collision the legs rest against each other
+    hip = lambda s: 2 * np.arccos(abs(s[10]))
+    assert hip(res[False][2]) > 0.3 and hip(res[True][2]) < 0.25   # without it they pass through to the PD target
