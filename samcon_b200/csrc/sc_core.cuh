@@ -25,16 +25,27 @@
 
 #if defined(__CUDACC__)
 #define SC_DEV __device__ __forceinline__
+// phase-level functions; measured on B200: making them real calls (__noinline__, 14.4k -> 13.1k SASS instructions)
+// was 3-5 % slower than inlining them into the step loop
+#define SC_PHASE __device__ __forceinline__
+#define SC_CALL __device__ __noinline__
 #define SC_SYNC() __syncwarp()
 // CTA-wide phase alignment.  Not needed for correctness (warps never share data): it keeps the warps of a CTA in
 // the same code region, because the step loop is ~170 KB of SASS and 8 warps at 8 different places in it starve
 // on instruction fetch (ncu: stalled_no_instruction 7.7 per issue on the walk workload without it, 0.2 with the
 // warps aligned).  Every warp of the CTA must execute the same number of these, see rollout_tile().
 #define SC_CTA_SYNC() __syncthreads()
+#ifndef SC_BAR_MASK
+#define SC_BAR_MASK 31
+#endif
+#define SC_BAR(bit) do { if (SC_BAR_MASK & (bit)) SC_CTA_SYNC(); } while (0)
 #else
 #define SC_DEV static inline
+#define SC_PHASE static
+#define SC_CALL static
 #define SC_SYNC() ((void)0)
 #define SC_CTA_SYNC() ((void)0)
+#define SC_BAR(bit) ((void)0)
 #endif
 
 // Optional phase timing (developer builds only: -DSC_PROFILE, tools/phase_profile.py).  SC_T(i) charges the cycles
@@ -116,7 +127,8 @@ constexpr int O_CB = O_SCR_END;                   // contact bodies (int): body 
 constexpr int O_CR = O_CB + MAXC;                 // contact point relative to the body origin, world axes (3)
 constexpr int O_CD = O_CR + 3 * MAXC;             // signed distance
 constexpr int O_NC = O_CD + MAXC;                 // number of contacts (int)
-constexpr int O_TM = O_NC + 1;                    // mask of bodies on a root path of some contact (int)
+constexpr int O_TM = O_NC + 1;                    // mask of bodies on a root path of some contact (int), | TM_TWO_BODY
+constexpr int TM_TWO_BODY = 1 << 30;              // some contact of the sample is link-vs-link
 constexpr int O_RHS = O_TM + 1;
 constexpr int O_LAM = O_RHS + NR;
 constexpr int O_END_DEV = O_LAM + NR;
@@ -342,7 +354,7 @@ SC_DEV void fk_body(float *S, const Tables &T, int b, bool full) {
 }
 
 template <class TT>
-SC_DEV void fk_sweep(float *sm, const TT &T, int L0, int L1, bool full) {
+SC_PHASE void fk_sweep(float *sm, const TT &T, int L0, int L1, bool full) {
     for (int d = 0; d < T.nlev; d++) {
         SC_STAGE {
             SC_LANE;
@@ -356,8 +368,7 @@ SC_DEV void fk_sweep(float *sm, const TT &T, int L0, int L1, bool full) {
 // ============================================================================================================
 // articulated-body algorithm (PD = stable-PD variant: pd inertia set, armature dt*Kd, O_TAU holds Kp err - Kd w)
 // ============================================================================================================
-template <bool PD>
-SC_DEV void aba_backward_body(float *S, const Tables &T, int b) {
+SC_DEV void aba_backward_body(float *S, const Tables &T, int b, const bool PD) {
     const float *I = (PD ? T.ipd : T.idyn) + 10 * b;
     const float m = I[0];
     const M3 R = ldM(S, O_RW + 9 * b);
@@ -442,8 +453,7 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b) {
     st3(S, O_PC + 6 * b + 3, paf);
 }
 
-template <bool PD>
-SC_DEV void aba_forward_body(float *S, const Tables &T, int b) {
+SC_DEV void aba_forward_body(float *S, const Tables &T, int b, const bool PD) {
     const int p = T.parent[b];
     const V3 r = ld3(S, O_RJ + 3 * b);
     const V3 alp = ld3(S, O_PC + 6 * p), ap = ld3(S, O_PC + 6 * p + 3);
@@ -466,21 +476,22 @@ SC_DEV void aba_forward_body(float *S, const Tables &T, int b) {
     }
 }
 
-template <bool PD, class TT>
-SC_DEV void aba(float *sm, const TT &T, int L0, int L1) {
+template <class TT>
+SC_PHASE void aba(float *sm, const TT &T, int L0, int L1, const bool PD) {
     for (int d = T.nlev - 1; d >= 0; d--) {
         SC_STAGE {
             SC_LANE;
             int b = T.level_start[d] + slot;
-            if (b < T.level_start[d + 1]) aba_backward_body<PD>(S, T, b);
+            if (b < T.level_start[d + 1]) aba_backward_body(S, T, b, PD);
         }
         SC_SYNC();
     }
+    SC_BAR(256);
     for (int d = 1; d < T.nlev; d++) {
         SC_STAGE {
             SC_LANE;
             int b = T.level_start[d] + slot;
-            if (b < T.level_start[d + 1]) aba_forward_body<PD>(S, T, b);
+            if (b < T.level_start[d + 1]) aba_forward_body(S, T, b, PD);
         }
         SC_SYNC();
     }
@@ -614,7 +625,7 @@ SC_DEV void write_contact(float *S, const Tables &T, const SelfTables &ST, int j
 }
 
 template <class TT>
-SC_DEV void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int L1 SC_PROF_ARGS) {
+SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int L1 SC_PROF_ARGS) {
     SC_STAGE {
         SC_LANE;
         const int c0 = slot * T.cand_per_lane;
@@ -779,13 +790,65 @@ SC_DEV void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int L1
     SC_SYNC();
 }
 
+// Column of the contact-space matrix for a sample whose contacts are all against the ground (the common case): one
+// body per contact, constant contact frame (n = +z, t1 = -y, t2 = +x), so directions and projections are components.
+SC_CALL void contact_column_ground(float *S, const Tables &T, int nc, int c) {
+    const int j = c / 3, k = c - 3 * j;
+    const int bj = f2i(F(O_CB + j)), dj = T.depth[bj];
+    const V3 f = k == 0 ? mk(0, 0, 1) : (k == 1 ? mk(0, -1, 0) : mk(1, 0, 0));
+    V3 pn = neg(cross(ld3(S, O_CR + 3 * j), f)), pf = neg(f);
+    V3 u[MAXLEV];
+#pragma unroll
+    for (int d = MAXLEV - 1; d >= 1; d--) {
+        u[d] = mk(0, 0, 0);
+        if (d <= dj) {
+            const int b = T.anc[bj][d];
+            u[d] = neg(pn);
+            const V3 Ku = mul(ldS(S, O_DI + 6 * b), u[d]);
+            pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
+            pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
+            pn = pn + cross(ld3(S, O_RJ + 3 * b), pf);
+        }
+    }
+    float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
+#pragma unroll
+    for (int i = 0; i < 21; i++) L[i] = F(O_I0L + i);
+    solve6(L, x);
+    int bprev = -1;
+    V3 aw = mk(0, 0, 0), al = mk(0, 0, 0);
+    for (int i = j; i < nc; i++) {
+        const int bi = f2i(F(O_CB + i));
+        if (bi != bprev) {
+            bprev = bi;
+            const int di = T.depth[bi];
+            aw = mk(x[0], x[1], x[2]); al = mk(x[3], x[4], x[5]);
+#pragma unroll
+            for (int d = 1; d < MAXLEV; d++) {
+                if (d <= di) {
+                    const int b = T.anc[bi][d];
+                    al = al + cross(aw, ld3(S, O_RJ + 3 * b));
+                    const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);
+                    const V3 qdd = mul(ldS(S, O_DI + 6 * b), uu - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
+                    aw = aw + qdd;
+                }
+            }
+        }
+        const V3 a = al + cross(aw, ld3(S, O_CR + 3 * i));
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) {
+            const int rr = 3 * i + kk;
+            if (rr >= c) F(O_AM + rr * (rr + 1) / 2 + c) = kk == 0 ? a.z : (kk == 1 ? -a.y : a.x);
+        }
+    }
+}
+
 // One column of the contact-space matrix A = J M^-1 J^T, computed by one lane without barriers: the response of
 // the articulated system (inertias left in shared memory by the dynamics ABA) to a unit impulse along direction k
 // of contact j.  The impulse walks up the tree to the root (recording u = -S^T p per level in registers), the 6x6
 // base block is solved with the Cholesky factor kept from the ABA, and accelerations walk back down to the bodies
 // of the contacts i >= j; rows >= the column index land in the packed lower triangle O_AM.  A link-vs-link contact
 // is the superposition of two such single-body problems (+f on body a, -f on body b): the second pass adds.
-SC_DEV void contact_column(float *S, const Tables &T, int nc, int c) {
+SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
     const int j = c / 3, k = c - 3 * j;
     const int cbj = f2i(F(O_CB + j));
     const V3 f0 = contact_frame_of(S, j, cbj).d[k];
@@ -916,7 +979,8 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
 #endif
 
 template <class TT>
-SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_PROF_ARGS) {
+SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, const int part SC_PROF_ARGS) {
+    if (part == 0) {
     // ---- right-hand sides from the predicted velocities; mask of the bodies on a contact's root path ------------
     SC_STAGE {
         SC_LANE;
@@ -936,7 +1000,7 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
             int mask = 0;
             for (int j = 0; j < nc; j++) {
                 const int cb = f2i(F(O_CB + j));
-                mask |= T.anc_mask[cb_a(cb)] | (cb_b(cb) >= 0 ? T.anc_mask[cb_b(cb)] : 0);
+                mask |= T.anc_mask[cb_a(cb)] | (cb_b(cb) >= 0 ? T.anc_mask[cb_b(cb)] | TM_TWO_BODY : 0);
             }
             F(O_TM) = i2f(mask);
         }
@@ -950,10 +1014,17 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
     SC_STAGE {
         SC_LANE;
         const int nc = f2i(F(O_NC));
+#if !defined(SC_TWO_COLUMNS)
         for (int c = slot; c < 3 * nc; c += QUAD) contact_column(S, T, nc, c);
+#else
+        if (f2i(F(O_TM)) & TM_TWO_BODY) for (int c = slot; c < 3 * nc; c += QUAD) contact_column(S, T, nc, c);
+        else for (int c = slot; c < 3 * nc; c += QUAD) contact_column_ground(S, T, nc, c);
+#endif
     }
     SC_SYNC();
     SC_T(8);
+    }
+    if (part == 1) {
     // ---- projected Gauss-Seidel, Bullet row order: all normals, then the friction pairs -------------------------
 #if defined(__CUDACC__)
     if (ncmax <= 2) gs_registers<2>(sm, T);
@@ -1010,6 +1081,8 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
         SC_SYNC();
     }
 #endif
+    }
+    if (part != 2) return;
     // ---- apply the impulses: one articulated response over the tree ------------------------------------------
     for (int d = T.nlev - 1; d >= 0; d--) {
         SC_STAGE {
@@ -1078,9 +1151,12 @@ SC_DEV void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax SC_P
 // integration (semi-implicit Euler, exponential-map quaternion update, Bullet's velocity clamp)
 // ============================================================================================================
 SC_DEV void quat_step(float *S, int o, V3 w, float h, bool left) {
-    const float a = sqrtf(dot(w, w));
-    const float s = a < 1e-3f ? 0.5f * h - h * h * h * 0.020833333333f * a * a : sinf(0.5f * a * h) / a;
-    const float ex = w.x * s, ey = w.y * s, ez = w.z * s, ew = cosf(0.5f * a * h);
+    // exp(h w / 2): the half angle x = |w| h / 2 is at most 0.5 * sqrt(3) * maxvel * h (0.043 at the reference settings),
+    // where the degree-7/6 Taylor polynomials are exact to float rounding (next terms x^8/9! and x^8/8! relative)
+    const float x2 = 0.25f * h * h * dot(w, w);
+    const float s = 0.5f * h * (1.0f + x2 * (-1.0f / 6.0f + x2 * (1.0f / 120.0f - x2 * (1.0f / 5040.0f))));     // sin(x) / |w|
+    const float ew = 1.0f + x2 * (-0.5f + x2 * (1.0f / 24.0f - x2 * (1.0f / 720.0f)));                           // cos(x)
+    const float ex = w.x * s, ey = w.y * s, ez = w.z * s;
     const float qx = F(o), qy = F(o + 1), qz = F(o + 2), qw = F(o + 3);
     float x, y, z, ww;
     if (left) {   // e (x) q
@@ -1095,7 +1171,7 @@ SC_DEV void quat_step(float *S, int o, V3 w, float h, bool left) {
 }
 
 template <class TT>
-SC_DEV void integrate(float *sm, const TT &T, int L0, int L1) {
+SC_PHASE void integrate(float *sm, const TT &T, int L0, int L1) {
     SC_STAGE {
         SC_LANE;
         const float mv = T.maxvel, h = T.h;
@@ -1157,7 +1233,7 @@ SC_DEV void load_state(float *sm, const TT &T, int L0, int L1, const float *rows
 // (humanoid_stable_pd.py:167-187, 218-222)
 // ============================================================================================================
 template <class TT>
-SC_DEV void features(float *sm, const TT &T, int L0, int L1) {
+SC_PHASE void features(float *sm, const TT &T, int L0, int L1) {
     fk_sweep(sm, T, L0, L1, true);
     SC_STAGE {
         SC_LANE;
@@ -1245,15 +1321,15 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
     if (tile0 >= a.S) {
         // a warp without a tile in this round only keeps the CTA's phase barriers company
         for (int step = 0; step < a.nsteps; step++) {
-            SC_CTA_SYNC();
-            for (int sub = 0; sub < T.nsub; sub++) { SC_CTA_SYNC(); SC_CTA_SYNC(); SC_CTA_SYNC(); }
+            SC_BAR(1); SC_BAR(256);
+            for (int sub = 0; sub < T.nsub; sub++) { SC_BAR(2); SC_BAR(256); SC_BAR(4); SC_BAR(64); SC_BAR(16); SC_BAR(32); SC_BAR(8); }
         }
         return;
     }
     load_state(sm, T, L0, L1, a.parents, a.parent_idx, a.children, tile0, a.S);
     SC_T(0);
     for (int step = 0; step < a.nsteps; step++) {
-        SC_CTA_SYNC();
+        SC_BAR(1);
         SC_T(13);
         fk_sweep(sm, T, L0, L1, true);
         SC_T(1);
@@ -1266,15 +1342,15 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
         }
         SC_SYNC();
         SC_T(2);
-        aba<true>(sm, T, L0, L1);
+        aba(sm, T, L0, L1, true);
         SC_T(3);
         for (int sub = 0; sub < T.nsub; sub++) {
-            SC_CTA_SYNC();
+            SC_BAR(2);
             SC_T(13);
             if (sub) { fk_sweep(sm, T, L0, L1, true); SC_T(1); }
-            aba<false>(sm, T, L0, L1);
+            aba(sm, T, L0, L1, false);
             SC_T(5);
-            SC_CTA_SYNC();
+            SC_BAR(4);
             SC_T(13);
             // positions are those of the start of the sub-step; the ABA's scratch is free for the collision pass now
             collide(sm, T, T.self, L0, L1 SC_PROF_PASS);
@@ -1283,13 +1359,20 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
 #if defined(SC_PROFILE) && defined(__CUDACC__)
             sc_prof_acc[16]++; sc_prof_acc[17] += ncmax > 0; sc_prof_acc[18 + (ncmax + 1) / 2]++;
 #endif
+            SC_BAR(64);
+            SC_T(13);
             if (ncmax > 0) {
                 fk_sweep(sm, T, L0, L1, false);
                 SC_T(6);
-                contact_solve(sm, T, L0, L1, ncmax SC_PROF_PASS);
-                SC_T(10);
+                contact_solve(sm, T, L0, L1, ncmax, 0 SC_PROF_PASS);
             }
-            SC_CTA_SYNC();
+            SC_BAR(16);
+            SC_T(13);
+            if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 1 SC_PROF_PASS); SC_T(9); }
+            SC_BAR(32);
+            SC_T(13);
+            if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 2 SC_PROF_PASS); SC_T(10); }
+            SC_BAR(8);
             SC_T(13);
             integrate(sm, T, L0, L1);
             SC_T(11);

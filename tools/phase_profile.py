@@ -17,7 +17,8 @@ from samcon_b200.pool import GpuSamplePool
 from helpers import stand, near_action, rand_state
 NAMES = ["load", "fk", "pd_term", "aba_pd", "collide", "aba", "fk_vel", "c_rhs", "c_assembly", "c_gs", "c_apply", "integrate",
          "features+cost+store", "cta_barrier_wait", "-", "idle/other"]
-cfg = Config("walk"); ch = Character.from_config(cfg); pool = GpuSamplePool(ch, 0)
+from samcon_b200.model import SimParams
+cfg = Config("walk"); ch = Character.from_config(cfg, SimParams(self_collision=os.environ.get("SC_SELF", "1") == "1")); pool = GpuSamplePool(ch, 0)
 pool._lib.sc_prof_read.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
 rng = np.random.default_rng(0)
 args = sys.argv[1:]

@@ -8,7 +8,8 @@ from samcon_b200.model import Character
 from samcon_b200.pool import GpuSamplePool
 from helpers import stand, near_action, rand_state
 
-cfg = Config("walk"); ch = Character.from_config(cfg); pool = GpuSamplePool(ch, 0)
+from samcon_b200.model import SimParams
+cfg = Config("walk"); ch = Character.from_config(cfg, SimParams(self_collision=os.environ.get("SC_SELF", "1") == "1")); pool = GpuSamplePool(ch, 0)
 print(pool.rollout_config())
 rng = np.random.default_rng(0)
 for mode in ("stand", "air"):
