@@ -1351,7 +1351,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             aba(sm, T, L0, L1, false);
             SC_T(5);
             SC_BAR(4);
-            SC_T(13);
+            SC_T(30);
             // positions are those of the start of the sub-step; the ABA's scratch is free for the collision pass now
             collide(sm, T, T.self, L0, L1 SC_PROF_PASS);
             SC_T(4);
@@ -1360,20 +1360,20 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             sc_prof_acc[16]++; sc_prof_acc[17] += ncmax > 0; sc_prof_acc[18 + (ncmax + 1) / 2]++;
 #endif
             SC_BAR(64);
-            SC_T(13);
+            SC_T(26);
             if (ncmax > 0) {
                 fk_sweep(sm, T, L0, L1, false);
                 SC_T(6);
                 contact_solve(sm, T, L0, L1, ncmax, 0 SC_PROF_PASS);
             }
             SC_BAR(16);
-            SC_T(13);
+            SC_T(27);
             if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 1 SC_PROF_PASS); SC_T(9); }
             SC_BAR(32);
-            SC_T(13);
+            SC_T(28);
             if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 2 SC_PROF_PASS); SC_T(10); }
             SC_BAR(8);
-            SC_T(13);
+            SC_T(29);
             integrate(sm, T, L0, L1);
             SC_T(11);
         }

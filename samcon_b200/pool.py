@@ -129,12 +129,15 @@ class GpuSamplePool:
         self._check(self._lib.sc_cost(self._h, _ptr(sim), _ptr(kin), sim.shape[0], _ptr(out), self._stream()), "sc_cost")
         return out
 
-    def sample_gen(self, target, limits, S, noise=None, perm=None, gaussian=False, seed=0, window=0):
+    def sample_gen(self, target, limits, S, noise=None, perm=None, gaussian=False, seed=0, window=0, out=None):
         target = self._f32(target, (STATE_DIM,))
         limits = self._f32(limits, (3 * self.nj,))
         noise = self._f32(noise, (S, 3 * self.nj)) if noise is not None else None
         perm = self._i32(perm)
-        out = torch.empty((S, self.act_dim), device=self.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty((S, self.act_dim), device=self.device, dtype=torch.float32)
+        elif tuple(out.shape) != (S, self.act_dim) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+            raise ValueError("out must be a contiguous float32 [S, 4*nj] tensor on the pool's device")
         rc = self._lib.sc_sample_gen(self._h, _ptr(target), _ptr(limits), _ptr(noise), _ptr(perm), int(bool(gaussian)),
                                      C.c_uint64(int(seed)), C.c_uint64(int(window)), int(S), _ptr(out), self._stream())
         self._check(rc, "sc_sample_gen")

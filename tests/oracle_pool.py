@@ -22,3 +22,51 @@ class OraclePool:
 
     def close(self):
         pass
+
+
+class OracleDevicePool:
+    """CPU stand-in for GpuSamplePool's device-level API (window / select / gather_rows / sample_gen on torch CPU
+    tensors, arithmetic by the oracle and the host sampler): lets the batched multi-sequence loop run without a GPU."""
+
+    def __init__(self, oracle, cfg):
+        import torch
+        self.o, self.cfg, self.torch = oracle, cfg, torch
+        self.device = torch.device("cpu")
+        self.nj = oracle.nj
+        self.act_dim = 4 * self.nj
+
+    def sample_gen(self, target, limits, S, noise=None, perm=None, gaussian=False, seed=0, window=0, out=None):
+        from samcon_b200.sampling import get_batch_action
+        rs = np.random.RandomState((int(seed) * 1000003 + int(window)) % (2 ** 31))
+        a = get_batch_action(np.asarray(target, np.float64), S, np.asarray(limits, np.float64), "gaussian" if gaussian else "uniform", rs)
+        t = self.torch.tensor(a, dtype=self.torch.float32)
+        if out is not None:
+            out.copy_(t)
+            return out
+        return t
+
+    def window(self, parents, actions, targets, nsteps, children=None, parent_idx=None, sample_seq=None, out=None):
+        P = np.asarray(parents, np.float64); A = np.asarray(actions, np.float64)
+        T = np.asarray(targets, np.float64).reshape(-1, 132)
+        S = len(A)
+        pidx = np.asarray(parent_idx) if parent_idx is not None else np.arange(S) // (children or S // len(P))
+        seq = np.asarray(sample_seq) if sample_seq is not None else np.zeros(S, int)
+        st = np.zeros((S, 132)); cost = np.zeros(S); info = np.zeros((S, 5))
+        for k in range(S):
+            s, c, i = self.o.window(P[pidx[k]][None], A[k][None], T[seq[k]], nsteps)
+            st[k], cost[k], info[k] = s[0], c[0], i[0]
+        f = lambda x: self.torch.tensor(x, dtype=self.torch.float32)
+        return f(st), f(cost), f(info)
+
+    def select(self, cost, E, seg_offsets=None):
+        c = np.asarray(cost, np.float64).reshape(-1)
+        seg = np.asarray(seg_offsets) if seg_offsets is not None else np.array([0, len(c)])
+        idx = np.zeros((len(seg) - 1, E), np.int32); ec = np.zeros((len(seg) - 1, E), np.float32)
+        for i in range(len(seg) - 1):
+            cs = c[seg[i]:seg[i + 1]]
+            o = np.lexsort((np.arange(len(cs)), cs))[:E]
+            idx[i] = seg[i] + o; ec[i] = cs[o]
+        return self.torch.tensor(idx), self.torch.tensor(ec)
+
+    def gather_rows(self, src, idx):
+        return src[self.torch.as_tensor(idx).reshape(-1).long()].contiguous()

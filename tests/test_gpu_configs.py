@@ -1,0 +1,105 @@
+"""GPU tests of BASELINE.json's other configs: cartwheel (hand/foot ground contact), multi-sequence batching with
+segmented elite selection, and full-size windows checked through size-independent properties (the oracle cannot
+follow at 10^5..10^6 rollouts)."""
+import numpy as np
+import pytest
+
+from helpers import joint_rms, near_action, stand
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cartwheel_window_parity(oracle):
+    """cartwheel.yml (cost weights [0,10,60,30,10], its own noise table): a window from the inverted phase of the
+    synthetic cartwheel, where hands carry the body -- capsule/box/sphere ground contacts on the arms."""
+    from oracle.oracle import Oracle
+    from samcon_b200.config import Config
+    from samcon_b200.model import Character
+    from samcon_b200.motion import AmassMotionData, make_synthetic_motion
+    from samcon_b200.pool import GpuSamplePool
+    from samcon_b200.sampling import get_batch_action
+    cfg = Config("cartwheel")
+    ch = Character.from_config(cfg)
+    o = Oracle(ch)
+    m = make_synthetic_motion("cartwheel", T=76, seed=0)
+    (name, _), = m.items()
+    ld = AmassMotionData(m, name)
+    pool = GpuSamplePool(ch, 0)
+    try:
+        checked = 0
+        for t0 in (0.9, 1.2, 1.5):                                   # hands reaching / on the ground, inverted, coming down
+            start, target = ld.getSpecTimeState(t0), ld.getSpecTimeState(t0 + 0.1)
+            E, children = 6, 4
+            parents = np.repeat(start[None], E, axis=0)
+            actions = get_batch_action(target, E * children, 0.25 * cfg.values, "uniform", np.random.RandomState(3))
+            st, cost, info = pool.window(parents.astype(np.float32), actions.astype(np.float32), target.astype(np.float32), 100)
+            ost, ocost, oinfo = o.window(parents, actions, target, 100)
+            rms = joint_rms(st.cpu().numpy(), ost)
+            crel = np.abs(cost.cpu().numpy() - ocost) / np.abs(ocost)
+            print(f"cartwheel t0={t0}: joint rms median {np.median(rms):.2e} max {rms.max():.2e}; cost rel max {crel.max():.2e}")
+            # hand-stand phases are contact-rich and occasionally chaotic: the bar is on the distribution
+            assert np.median(rms) < 1e-4 and (rms < 1e-3).mean() >= 0.75 and rms.max() < 0.1
+            assert np.median(crel) < 1e-4 and (crel < 1e-3).mean() >= 0.75
+            links = {int(r[0]) for s in ost for r in o.contacts_full(s) if r[1] < 0}
+            checked += len(links & {14, 15, 16, 18, 19, 20, 12, 13, 17})          # arm / hand links touched the ground
+        assert checked > 0
+    finally:
+        pool.close()
+
+
+def test_batched_sequences_equal_single_runs(pool, walk_cfg):
+    """Config 5: Q sequences in one launch per window == every sequence alone, bit for bit (per-sample arithmetic
+    does not depend on where a sample sits in the batch); segmented select keeps each sequence's own elites."""
+    from samcon_b200.batched import BatchedSamCon
+    from samcon_b200.motion import AmassMotionData, make_synthetic_motion
+    loaders = []
+    for seed in (0, 1, 2, 5):
+        m = make_synthetic_motion("walk", T=31, seed=seed)
+        (name, _), = m.items()
+        loaders.append(AmassMotionData(m, name))
+    kw = dict(nIter=3, nSample=60, nSave=6)
+    both = BatchedSamCon(walk_cfg, loaders, pool, **kw).sample()
+    for q in (0, 3):
+        # same Philox stream as sequence q had in the batch: seed = cfg.seed + q
+        import copy
+        cfg_q = copy.copy(walk_cfg)
+        cfg_q.seed = walk_cfg.seed + q
+        alone = BatchedSamCon(cfg_q, [loaders[q]], pool, **kw).sample()[0]
+        for key in ("simulated_state", "action", "cost", "elite_cost"):
+            np.testing.assert_array_equal(alone[key], both[q][key])
+    assert all((np.diff(r["elite_cost"], axis=1) >= 0).all() for r in both)
+
+
+def test_full_size_window_properties(pool, walk_cfg):
+    """10^5 rollouts x 100 steps (config 4's per-GPU order of magnitude): determinism, batch-position invariance
+    (the same (parent, action) pair gives the same bits wherever it sits), and top-k against torch.sort."""
+    import torch
+    rng = np.random.default_rng(11)
+    E, children = 10000, 10
+    S = E * children
+    base = np.array([stand(rng, 0.03, 0.1, 0.985) for _ in range(32)], dtype=np.float32)
+    acts = np.array([near_action(base[0], rng, 0.15) for _ in range(64)], dtype=np.float32)
+    parents = torch.tensor(base[rng.integers(0, 32, E)], device="cuda")
+    actions = torch.tensor(acts[rng.integers(0, 64, S)], device="cuda")
+    target = torch.tensor(stand(rng), dtype=torch.float32, device="cuda")
+    st, cost, info = pool.window(parents, actions, target, 100)
+    st2, cost2, info2 = pool.window(parents, actions, target, 100)
+    assert torch.equal(st, st2) and torch.equal(cost, cost2) and torch.equal(info, info2)
+    assert torch.isfinite(st).all() and torch.isfinite(cost).all()
+    # a random permutation of the samples (explicit parent_idx) permutes the outputs
+    perm = torch.randperm(S, device="cuda")
+    pidx = (perm // children).to(torch.int32)
+    stp, costp, _ = pool.window(parents, actions[perm].contiguous(), target, 100, parent_idx=pidx)
+    assert torch.equal(stp, st[perm]) and torch.equal(costp, cost[perm])
+    # cost is what sc_cost says about the final states
+    c6 = pool.cost(st[:4096], target)
+    assert torch.equal(c6[:, 0], cost[:4096]) and torch.equal(c6[:, 1:], info[:4096])
+    # elite selection: the E smallest, ascending by (cost, index)
+    idx, ec = pool.select(cost, E)
+    key = torch.argsort(cost, stable=True)[:E]
+    assert torch.equal(idx[0].long(), key) and torch.equal(ec[0], cost[key])
+    # segmented: 100 segments of 1000, 37 elites each
+    seg = torch.arange(0, S + 1, 1000, dtype=torch.int32, device="cuda")
+    idx, ec = pool.select(cost, 37, seg_offsets=seg)
+    ref = torch.argsort(cost.reshape(100, 1000), dim=1, stable=True)[:, :37] + seg[:-1, None].long()
+    assert torch.equal(idx.long(), ref)

@@ -114,3 +114,34 @@ def test_samcon_loop_on_oracle_pool(oracle, motion):
     assert np.array_equal(out2[name]["path_0"]["action"], p0["action"])
     with pytest.raises(Exception, match="multiples of nSave"):
         SamCon(cfg, loader, 1, 2, 21, 4, pool=OraclePool(oracle))
+
+
+def test_batched_multi_sequence_equals_single_runs(oracle):
+    """BASELINE config 5 (many sequences solved concurrently): one batched run over Q sequences must give every
+    sequence the path it gets when solved alone -- per-sequence targets, parents, segmented elite selection and the
+    back-trace are independent per sequence."""
+    from oracle_pool import OracleDevicePool
+    from samcon_b200.batched import BatchedSamCon
+    cfg = Config("walk")
+    pool = OracleDevicePool(oracle, cfg)
+    loaders = []
+    for seed in (0, 3):
+        m = make_synthetic_motion("walk", T=16, seed=seed)
+        (name, _), = m.items()
+        loaders.append(AmassMotionData(m, name))
+    kw = dict(nIter=2, nSample=12, nSave=3)
+    both = BatchedSamCon(cfg, loaders, pool, device_noise=False, **kw).sample()
+    assert len(both) == 2 and both[0]["simulated_state"].shape == (2, 132) and both[0]["action"].shape == (2, 68)
+    for q, ld in enumerate(loaders):
+        alone = BatchedSamCon(cfg, [ld], pool, device_noise=False, **kw).sample()[0]
+        for key in ("simulated_state", "action", "cost", "elite_cost", "target_state"):
+            np.testing.assert_array_equal(alone[key], both[q][key])
+        assert alone["total_cost"] == both[q]["total_cost"]
+    # elite costs ascend, the best path ends in the cheapest elite of the last window
+    assert (np.diff(both[0]["elite_cost"], axis=1) >= 0).all()
+    assert both[0]["cost"][-1] == both[0]["elite_cost"][-1, 0]
+    # Q = 1 with host noise is the reference loop: same elites as SamCon on the same pool arithmetic
+    cfg.motion_seq = "x"
+    ref = SamCon(cfg, loaders[0], 1, 2, 12, 3, pool=OraclePool(oracle))
+    out, info = ref.sample(save=False)
+    np.testing.assert_allclose(out["x"]["path_0"]["cost"].reshape(-1), both[0]["cost"], rtol=1e-5)

@@ -31,10 +31,12 @@ def report(tag, ms):
     pool._lib.sc_prof_read(pool._h, buf)
     v = np.array(list(buf), dtype=np.float64)
     ph, st = v[:16], v[16:]
-    tot = ph.sum()
+    tot = ph.sum() + v[26:31].sum()
     print(f"== {tag}: {ms:.2f} ms")
     for n, x in zip(NAMES, ph):
         if x: print(f"  {n:22s} {100*x/tot:6.2f}%")
+    for n, i in (("wait before collide (after aba)", 30), ("wait after collide", 26), ("wait after assembly", 27), ("wait after gs", 28), ("wait after apply", 29)):
+        if v[i]: print(f"  {n:32s} {100*v[i]/tot:6.2f}%")
     if st[0]:
         # per warp-substep statistics: st[0] substeps, st[1] with contacts, st[2..6] ncmax buckets 0,1-2,3-4,5-6,7-8,
         # st[7] overflow (some sample had more candidate hits than max_contacts), st[8] sum of per-sample nc (lane 0's)
