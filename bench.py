@@ -35,6 +35,10 @@ S_PER_GPU, E_PER_GPU, STEPS_PER_WINDOW = 10000, 1000, 100
 FLOP_PER_SAMPLE_STEP = 2.5e5      # F(n_c=4)
 BYTES_PER_SAMPLE_STEP = 21.0
 METRIC, UNIT = "humanoid sample-sim-steps/sec", "sample-steps/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload (S = 10 000, 100 steps), from the
+# committed `ncu --set full` capture; below the algorithmic 21 MB because one window's buffers sit in the 126 MB L2
+NCU_DRAM_BYTES_PER_LAUNCH = 6419968 + 755456
+NCU_DRAM_SOURCE = "profiles/r1n_walk_rollout_full.txt (ncu --set full, one launch, S=10000)"
 
 
 def workload_inputs(n_windows):
@@ -262,7 +266,9 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {"bound": "fp32-cuda-core (not hbm, not tensor: SURVEY.md §8d)", "achieved": kern_rate * FLOP_PER_SAMPLE_STEP / 1e12,
                 "peak": fp32_peak, "unit": "TFLOP/s", "frac": kern_rate * FLOP_PER_SAMPLE_STEP / 1e12 / fp32_peak,
-                "traffic": None, "kernel": "sc_rollout_kernel", "kernel_ms_per_launch": kernel_ms,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_DRAM_SOURCE,
+                "algorithmic_bytes_per_launch": S * STEPS_PER_WINDOW * BYTES_PER_SAMPLE_STEP,
+                "kernel": "sc_rollout_kernel", "kernel_ms_per_launch": kernel_ms,
                 "flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
                 "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json"
                                f"{'' if peaks else ' absent: fallback 1965'})",

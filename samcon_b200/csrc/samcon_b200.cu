@@ -9,7 +9,7 @@
 using namespace sc;
 
 // ============================================================================================================
-// rollout kernel: one warp = one tile of 8 samples, 4 lanes per sample, the whole window in shared memory
+// rollout kernel: one warp = one tile of 4 samples, 8 lanes per sample, 10 warps per CTA, the whole window in shared memory
 // ============================================================================================================
 constexpr int TABLE_WORDS = (sizeof(Tables) + 15) / 16 * 4;
 

@@ -1,10 +1,10 @@
 // sc_core.cuh -- per-sample humanoid rollout, written as "lane stages".
 //
-// Mapping: one sample is owned by a QUAD of 4 lanes; a warp carries a TILE of 8 samples.
-// lane = slot*8 + s  (s = sample in tile 0..7, slot = 0..3).  Bodies are numbered level by level and no tree
-// level is wider than 4, so in every tree sweep the quad's lane `slot` owns body level_start[d]+slot.
+// Mapping: one sample is owned by a group of QUAD = 8 lanes; a warp carries a TILE of 4 samples.
+// lane = slot*4 + s  (s = sample in tile 0..3, slot = 0..7).  Bodies are numbered level by level and no tree
+// level is wider than 4, so in every tree sweep the group's lane `slot` owns body level_start[d]+slot.
 // All per-sample working data lives in shared memory, interleaved so that word w of sample s sits at
-// sm[w*8+s] (the 8 samples of a tile hit 8 different banks; the <=4 bodies of a level have consecutive ids).
+// sm[w*4+s] (the 4 samples of a tile hit 4 different banks; the <=4 bodies of a level have consecutive ids).
 // A "stage" is a piece of straight-line per-lane code followed by a warp barrier; no per-lane value lives
 // across a barrier.  That discipline lets the same source be compiled for the host as a lane loop
 // (tests/emu, debugging aid only -- the package never loads it) and for sm_100a with __syncwarp().
@@ -305,7 +305,7 @@ SC_DEV void solve6(const float *L, float *x) {
     }
 }
 
-// max over the 8 samples of a tile of an int field; call between stages only
+// max over the samples of a tile of an int field; call between stages only
 SC_DEV int tile_max_int(const float *sm, int off) {
 #if defined(__CUDACC__)
     int v = f2i(sm[off * TILE + (threadIdx.x & (TILE - 1))]);
@@ -1298,7 +1298,7 @@ SC_DEV void cost_terms(const float *S, const Tables &T, const float *kin, const 
 }
 
 // ============================================================================================================
-// one tile = 8 samples through a whole SamCon window
+// one tile = 4 samples through a whole SamCon window
 // ============================================================================================================
 struct RolloutArgs {
     const float *parents;      // [E,132]

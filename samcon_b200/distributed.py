@@ -40,11 +40,12 @@ class ShardedSearch:
         lidx, lcost = lidx.reshape(-1), lcost.reshape(-1)
         if self.world == 1:
             return self.pool.gather_rows(st, lidx[:self.E]), lidx[:self.E].to(torch.int64), lcost[:self.E]
-        all_cost = torch.empty((self.world, self.Ec), dtype=torch.float32, device=dev)
-        all_idx = torch.empty((self.world, self.Ec), dtype=torch.int32, device=dev)
+        # flat [world * Ec] outputs: the layout both NCCL and gloo accept for a 1-D input
+        all_cost = torch.empty((self.world * self.Ec,), dtype=torch.float32, device=dev)
+        all_idx = torch.empty((self.world * self.Ec,), dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(all_cost, lcost.contiguous(), group=self.group)
         dist.all_gather_into_tensor(all_idx, lidx.contiguous(), group=self.group)
-        pos, gcost = self.pool.select(all_cost.reshape(-1), self.E)
+        pos, gcost = self.pool.select(all_cost, self.E)
         pos = pos.reshape(-1).to(torch.int64)
         win_rank = pos // self.Ec
         win_local = all_idx.reshape(-1)[pos].to(torch.int64)

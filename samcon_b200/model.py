@@ -12,7 +12,7 @@ is derived here once on the host:
   Either can be switched to the other (``inertia_dyn`` / ``inertia_pd`` options).
 * for the device: fixed joints folded into their parents (18 moving bodies for the SMPL
   humanoid), bodies renumbered level by level (all bodies of one tree depth are
-  consecutive) so that the 4 lanes that own one sample process one tree level per step.
+  consecutive) so that the lanes that own one sample process one tree level per step.
 """
 from __future__ import annotations
 
@@ -23,7 +23,7 @@ import numpy as np
 from .urdf import BOX, CAPSULE, SPHERE, J_FIXED, J_FLOATING, J_SPHERICAL, Link
 
 STATE_DIM = 132          # humanoid_stable_pd.py:142-148
-MAX_LEVEL_WIDTH = 4      # lanes per sample in the rollout kernel
+MAX_LEVEL_WIDTH = 4      # articulated-inertia hand-over slots per tree level in the rollout kernel (ICW)
 
 
 @dataclass
