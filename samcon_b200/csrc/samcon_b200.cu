@@ -29,9 +29,17 @@ __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *_
 #if defined(SC_PROFILE)
     long long sc_prof_acc[SC_NPHASE] = {}, sc_prof_last = clock64();
 #endif
-    // every warp of the CTA runs the same number of rounds (rollout_tile has CTA-wide phase barriers)
-    for (int base = blockIdx.x * WPB; base < ntiles; base += gridDim.x * WPB)
-        rollout_tile(sm, T, a, (base + warp) * TILE, lane, lane + 1 SC_PROF_PASS);
+    // Tiles are dealt evenly to the CTAs, and a CTA spreads its tiles evenly over its rounds (17 tiles: 9 + 8, not
+    // 10 + 7), so the last round is not a few full CTAs next to idle SMs.  Every warp of the CTA runs every round
+    // (rollout_tile has CTA-wide phase barriers); a warp without a tile passes tile0 >= S.
+    const int per = ntiles / gridDim.x, extra = ntiles % gridDim.x;
+    const int mine = per + ((int)blockIdx.x < extra ? 1 : 0), first = blockIdx.x * per + min((int)blockIdx.x, extra);
+    const int rounds = (mine + WPB - 1) / WPB, wpr = rounds ? (mine + rounds - 1) / rounds : 0;
+    for (int r = 0; r < rounds; r++) {
+        const int t = r * wpr + warp;
+        const bool active = warp < wpr && t < mine;
+        rollout_tile(sm, T, a, active ? (first + t) * TILE : a.S, lane, lane + 1 SC_PROF_PASS);
+    }
 #if defined(SC_PROFILE)
     if (lane == 0 && a.prof)
         for (int i = 0; i < SC_NPHASE; i++) atomicAdd((unsigned long long *)a.prof + i, (unsigned long long)sc_prof_acc[i]);
@@ -283,8 +291,9 @@ static int sc_reserve(sc_context *h, T **p, size_t *cap, size_t need) {
 
 static int sc_launch_rollout(sc_context *h, const RolloutArgs &a, cudaStream_t st) {
     const int ntiles = (a.S + TILE - 1) / TILE;
-    int grid = (ntiles + WPB - 1) / WPB;
-    if (grid > h->grid_cap) grid = h->grid_cap;
+    // all SMs even when there are few tiles (walk.yml's own nSample = 2000 is 500 tiles: 3-4 warps on each of 148 SMs
+    // beat 10 warps on 50 of them); the kernel deals the tiles evenly
+    const int grid = ntiles < h->grid_cap ? ntiles : h->grid_cap;
 #if defined(SC_PROFILE)
     RolloutArgs ap = a;
     if (!h->d_prof) { cudaMalloc(&h->d_prof, SC_NPHASE * sizeof(long long)); cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long)); }
