@@ -254,6 +254,27 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = world * S * STEPS_PER_WINDOW * K / e2e_s.item()
 
+    # ------------------------------------------------------------------ BASELINE metric (ii): seconds per SamCon window at
+    # walk.yml's own size (nSample 2000, nSave 200), through the host API like the e2e arm; rank 0, N = 1 only
+    walk_window_s = None
+    if world == 1:
+        S2, E2 = cfg.nSample, cfg.nSave
+        acts2 = [torch.from_numpy(get_batch_action(targets[w], S2, cfg.values, cfg.noise_type, rs).astype(np.float32)).pin_memory()
+                 for w in range(1, W + K + 1)]
+        pool.init(targets[0], E2)
+
+        def walk_step(w):
+            st, cost, info = pool.sim(targets[w], acts2[w - 1], STEPS_PER_WINDOW)
+            pool.keep(pool.select_last(E2))
+        for w in range(1, W + 1):
+            walk_step(w)
+        torch.cuda.synchronize(dev)
+        c0 = time.perf_counter()
+        for w in range(W + 1, W + K + 1):
+            walk_step(w)
+        torch.cuda.synchronize(dev)
+        walk_window_s = (time.perf_counter() - c0) / K
+
     value = world * S * STEPS_PER_WINDOW * K / (ms_total * 1e-3)
     kern_rate = S * STEPS_PER_WINDOW / (kernel_ms * 1e-3)       # one GPU's rollout kernel
     peaks = {}
@@ -282,7 +303,8 @@ def run_ours(args):
                                    "(dt 1 ms, 2 sub-steps, 10 solver iters), synthetic SMPL-shaped walk",
                        "nSample_per_gpu": S, "nSave_per_gpu": E, "steps_per_window": STEPS_PER_WINDOW,
                        "l2": "256 MB memset between steps (inside the timed region)", "parallelism": f"samples sharded x{world}",
-                       "best_elite_cost_last_window": best_cost},
+                       "best_elite_cost_last_window": best_cost,
+                       "walk_yml_window_s_at_nSample_2000": walk_window_s},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": S * 68 * 4 + 132 * 4,
                     "d2h_bytes_per_step": S * (132 + 1 + 5) * 4 + E * 8},
