@@ -174,9 +174,11 @@ class Character:
     def from_config(cls, cfg, sim: SimParams | None = None, **kw):
         from .urdf import load_links
         links = load_links(cfg.model_file, cfg.scale, search_dirs=(getattr(cfg, "base_dir", ""),))
+        if sim is None:     # cfg key self_collision (walk.yml:113) -> loadURDF flags, humanoid_stable_pd.py:10-13
+            sim = SimParams(self_collision=bool(getattr(cfg, "self_collision", True)))
         return cls(links, cfg.kps, cfg.kds, cfg.max_forces, np.asarray(cfg.joint_weights, dtype=np.float64),
                    list(cfg.end_effectors), np.asarray(cfg.cost_weights, dtype=np.float64), float(cfg.height),
-                   sim or SimParams(), **kw)
+                   sim, **kw)
 
     # ------------------------------------------------------------------ oracle tables
     def raw_tables(self):

@@ -17,7 +17,7 @@ import time
 import numpy as np
 
 from .model import Character
-from .sampling import get_batch_action
+from .sampling import draw_noise, get_batch_action
 from .trajectory import Trajectory
 
 
@@ -44,7 +44,7 @@ def get_eta_str(cur_iter, total_iter, time_per_iter):     # /root/reference/util
 class SamCon:
 
     def __init__(self, cfg, data_loader, num_processes=1, nIter=None, nSample=None, nSave=None, pool=None, logger=None,
-                 device_select=True):
+                 device_select=True, device_actions=True):
         """``num_processes`` is accepted for call compatibility (run_samcon.py:36); the GPU pool replaces the
         process pool, so its value is not used.  ``pool`` may be any object with init/sim/keep/close (the
         tests pass an oracle-backed one); by default a GpuSamplePool on cuda:0 is created."""
@@ -67,6 +67,7 @@ class SamCon:
             pool = GpuSamplePool(Character.from_config(cfg), 0)
         self._pool = pool
         self._device_select = device_select and hasattr(pool, "select_last")
+        self._device_actions = device_actions and hasattr(pool, "sample_gen") and cfg.noise_type == "uniform"
         self._unique_id = UniqueId()
         self._traj = Trajectory(self._nIter, self._nSample, self._nSave)
         self._logger = logger or logging.getLogger("samcon_b200")
@@ -87,11 +88,23 @@ class SamCon:
         for t in range(1, self._nIter + 1):
             t0 = time.time()
             target_state = self._data_loader.getSpecTimeState(t * self._sample_timestep)
-            batch_action = self.get_batch_action(target_state)
+            if self._device_actions:
+                # same MT19937 draws and shuffle as get_batch_action (samcon.py:113-118, 140); the Euler <-> quaternion
+                # arithmetic (samcon.py:121-137) runs on the device (sc_sample_gen) instead of scipy on the host
+                noise, perm = draw_noise(self._nSample, self._cfg.values, self._cfg.noise_type, self._rng)
+                dev_action = self._pool.sample_gen(np.asarray(target_state, dtype=np.float32),
+                                                   np.asarray(self._cfg.values, dtype=np.float32), self._nSample,
+                                                   noise=noise.astype(np.float32), perm=perm.astype(np.int32))
+                batch_action = None
+            else:
+                batch_action = self.get_batch_action(target_state)
+                dev_action = batch_action
             prev_uids = self._traj.get_curr_uid_elite(t - 1)
             curr_uids = np.fromiter(self._unique_id.get(self._nSample), dtype=np.int64, count=self._nSample)
             # sample k descends from elite k // num_substep (samcon.py:31-35, 85-90)
-            sim_state, cost, info = self._pool.sim(target_state, batch_action, self._steps_per_window)
+            sim_state, cost, info = self._pool.sim(target_state, dev_action, self._steps_per_window)
+            if batch_action is None:
+                batch_action = dev_action.cpu().numpy().astype(np.float64)
             self._traj.push_batch(t, np.repeat(prev_uids, self._num_substep), curr_uids, target_state, sim_state,
                                   batch_action, cost, info)
             elite = self._pool.select_last(self._nSave) if self._device_select else None
