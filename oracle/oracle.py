@@ -161,6 +161,12 @@ class Oracle:
     def num_pairs(self):
         return lib().oc_num_pairs(self._h)
 
+    def last_ground_impulse(self):
+        """Sum of the ground-contact impulses (world x, y, z) of the last sub-step run in this thread."""
+        out = np.zeros(3)
+        lib().oc_last_ground_impulse(out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
     def step_torque(self, state, tau, nsub_total):
         s, sp = _d(np.array(state, dtype=np.float64, copy=True))
         lib().oc_step_torque(self._h, sp, _d(tau)[1], C.c_int(nsub_total))

@@ -558,6 +558,7 @@ static void plane_space(const double *n, double *p, double *q) {
  * /root/reference/envs/humanoid_tracking_env.py:187-189: actuate(action); stepSimulation().
  * numSubSteps internal steps of dt/numSubSteps; torque from the stable-PD solve is held across them. */
 static int g_last_contacts = 0;
+static double g_last_normal_impulse = 0, g_last_tangent_impulse[2] = {0, 0};   /* diagnostics: last sub-step, ground contacts */
 
 static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const double *tau, double h) {
     static __thread double M[MAXV * MAXV], MinvJt[MAXROW][MAXV], J[MAXROW][MAXV];
@@ -612,7 +613,12 @@ static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const doub
                 }
         }
         for (int i = 0; i < nv; i++) v[i] += dv[i];
-    }
+        g_last_normal_impulse = 0; g_last_tangent_impulse[0] = g_last_tangent_impulse[1] = 0;
+        for (int c = 0; c < nc; c++) if (con[c].link2 < 0) {
+            g_last_normal_impulse += lam[3 * c];
+            g_last_tangent_impulse[0] += lam[3 * c + 2]; g_last_tangent_impulse[1] -= lam[3 * c + 1];   /* world x, y */
+        }
+    } else { g_last_normal_impulse = 0; g_last_tangent_impulse[0] = g_last_tangent_impulse[1] = 0; }
     /* back to the stored representation, clamp, integrate (semi-implicit Euler) */
     mv3(k->R[0], v, st->ww);
     mv3(k->R[0], v + 3, st->vw);
@@ -655,6 +661,7 @@ void oc_step(const oc_model *m, double *state, const double *action, int nsteps)
     pack(m, &st, state);
 }
 int oc_last_contacts(void) { return g_last_contacts; }
+void oc_last_ground_impulse(double *out3) { out3[0] = g_last_tangent_impulse[0]; out3[1] = g_last_tangent_impulse[1]; out3[2] = g_last_normal_impulse; }
 
 /* ------------------------------------------------------------------ cost
  * /root/reference/envs/humanoid_tracking_env.py:78-176 (formulas in SURVEY.md §9.4);

@@ -143,3 +143,14 @@ def test_self_contact_window(pool, oracle):
     assert rms.max() < JOINT_TOL
     np.testing.assert_allclose(st[:, :3], ost[:, :3], atol=2e-4)
     np.testing.assert_allclose(cost, ocost, rtol=COST_RTOL)
+
+
+def test_committed_fixture_windows(pool):
+    """The committed oracle fixtures (tests/golden/oracle_windows.npz) through the C ABI: the GPU path against
+    numbers that travel with the repo (the walk-cfg scenarios; the pool is built from walk.yml)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_windows.npz"))
+    for key in ("air", "stand", "self"):
+        st, cost, info = _run(pool, g[f"{key}_parents"], g[f"{key}_actions"], g[f"{key}_target"], int(g[f"{key}_nsteps"]), 1)
+        assert joint_rms(st, g[f"{key}_state"]).max() < JOINT_TOL
+        np.testing.assert_allclose(cost, g[f"{key}_cost"], rtol=COST_RTOL)

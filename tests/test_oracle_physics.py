@@ -193,3 +193,39 @@ def test_self_contact_conserves_momentum_and_separates(walk_cfg):
     assert res[True][1] > -0.01            # with self collision the legs rest against each other
     hip = lambda s: 2 * np.arccos(abs(s[10]))
     assert hip(res[False][2]) > 0.3 and hip(res[True][2]) < 0.25   # without it they pass through to the PD target
+
+
+def test_oracle_regression_fixtures():
+    """tests/golden/oracle_windows.npz: the restatement's own outputs on seeded windows (a regression pin of the
+    oracle, NOT a reference golden -- DESIGN.md §6).  Regenerate with tests/golden/make_oracle_golden.py."""
+    import os
+    from oracle.oracle import Oracle
+    from samcon_b200.config import Config
+    from samcon_b200.model import Character
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_windows.npz"))
+    for key, cfgname in (("air", "walk"), ("stand", "walk"), ("self", "walk"), ("cartwheel", "cartwheel")):
+        o = Oracle(Character.from_config(Config(cfgname)))
+        st, cost, info = o.window(g[f"{key}_parents"], g[f"{key}_actions"], g[f"{key}_target"], int(g[f"{key}_nsteps"]))
+        np.testing.assert_allclose(st, g[f"{key}_state"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(cost, g[f"{key}_cost"], rtol=1e-9)
+        np.testing.assert_allclose(info, g[f"{key}_info"], rtol=1e-8, atol=1e-12)
+
+
+def test_standing_ground_reaction_carries_the_weight(oracle, character):
+    """First-principles check of dynamics + contact together: once a standing humanoid has settled, the ground's
+    normal impulse per sub-step is weight x h (the CoM does not accelerate vertically) and the horizontal one stays a
+    few per cent of it (the passive stand leans slowly), far inside the friction pyramid."""
+    rng = np.random.default_rng(3)
+    s = stand(rng, 0.0, 0.0, 0.99)
+    s[0:2] = 0
+    a = s[7:75].copy()
+    s = oracle.step(s, a, 400)
+    imp = []
+    for _ in range(100):
+        s = oracle.step(s, a, 1)
+        imp.append(oracle.last_ground_impulse())
+    imp = np.array(imp)
+    h = character.sim.dt / character.sim.num_substeps
+    weight = sum(l.mass for l in character.links) * 9.8
+    assert abs(imp[:, 2].mean() / h - weight) / weight < 0.01
+    assert np.abs(imp[:, :2].mean(axis=0) / h).max() < 0.1 * weight < character.sim.friction * weight
