@@ -103,3 +103,27 @@ def test_full_size_window_properties(pool, walk_cfg):
     idx, ec = pool.select(cost, 37, seg_offsets=seg)
     ref = torch.argsort(cost.reshape(100, 1000), dim=1, stable=True)[:, :37] + seg[:-1, None].long()
     assert torch.equal(idx.long(), ref)
+
+
+def test_replay_determinism(pool, walk_cfg):
+    """The reference's own check (scripts/eval_samcon.py:60, 67-81, 107-111): replaying path_0's actions from
+    t0_state through the env facade reproduces the stored simulated states and costs -- here bit for bit, because a
+    sample's state is exactly its 132 floats (stateless contacts) and results do not depend on batch position."""
+    import copy
+    from samcon_b200.envs import HumanoidTrackingEnv
+    from samcon_b200.motion import AmassMotionData, make_synthetic_motion
+    from samcon_b200.samcon import SamCon
+    cfg = copy.copy(walk_cfg)
+    m = make_synthetic_motion("walk", T=31, seed=4)
+    (name, _), = m.items()
+    cfg.motion_seq = name
+    sc = SamCon(cfg, AmassMotionData(m, name), 1, nIter=4, nSample=200, nSave=20, pool=pool)
+    out, info = sc.sample(save=False)
+    p = out[name]["path_0"]
+    env = HumanoidTrackingEnv(cfg, False, pool=pool)
+    env._sim_agent.set_state(p["t0_state"])
+    for i in range(4):
+        env._kin_agent.set_state(p["target_state"][i])
+        state, cost, terms = env.step(p["action"][i])
+        np.testing.assert_array_equal(state.astype(np.float32), p["simulated_state"][i].astype(np.float32))
+        assert np.float32(cost) == np.float32(p["cost"][i])
