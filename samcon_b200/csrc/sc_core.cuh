@@ -790,58 +790,6 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
     SC_SYNC();
 }
 
-// Column of the contact-space matrix for a sample whose contacts are all against the ground (the common case): one
-// body per contact, constant contact frame (n = +z, t1 = -y, t2 = +x), so directions and projections are components.
-SC_CALL void contact_column_ground(float *S, const Tables &T, int nc, int c) {
-    const int j = c / 3, k = c - 3 * j;
-    const int bj = f2i(F(O_CB + j)), dj = T.depth[bj];
-    const V3 f = k == 0 ? mk(0, 0, 1) : (k == 1 ? mk(0, -1, 0) : mk(1, 0, 0));
-    V3 pn = neg(cross(ld3(S, O_CR + 3 * j), f)), pf = neg(f);
-    V3 u[MAXLEV];
-#pragma unroll
-    for (int d = MAXLEV - 1; d >= 1; d--) {
-        u[d] = mk(0, 0, 0);
-        if (d <= dj) {
-            const int b = T.anc[bj][d];
-            u[d] = neg(pn);
-            const V3 Ku = mul(ldS(S, O_DI + 6 * b), u[d]);
-            pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
-            pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
-            pn = pn + cross(ld3(S, O_RJ + 3 * b), pf);
-        }
-    }
-    float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
-#pragma unroll
-    for (int i = 0; i < 21; i++) L[i] = F(O_I0L + i);
-    solve6(L, x);
-    int bprev = -1;
-    V3 aw = mk(0, 0, 0), al = mk(0, 0, 0);
-    for (int i = j; i < nc; i++) {
-        const int bi = f2i(F(O_CB + i));
-        if (bi != bprev) {
-            bprev = bi;
-            const int di = T.depth[bi];
-            aw = mk(x[0], x[1], x[2]); al = mk(x[3], x[4], x[5]);
-#pragma unroll
-            for (int d = 1; d < MAXLEV; d++) {
-                if (d <= di) {
-                    const int b = T.anc[bi][d];
-                    al = al + cross(aw, ld3(S, O_RJ + 3 * b));
-                    const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);
-                    const V3 qdd = mul(ldS(S, O_DI + 6 * b), uu - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
-                    aw = aw + qdd;
-                }
-            }
-        }
-        const V3 a = al + cross(aw, ld3(S, O_CR + 3 * i));
-#pragma unroll
-        for (int kk = 0; kk < 3; kk++) {
-            const int rr = 3 * i + kk;
-            if (rr >= c) F(O_AM + rr * (rr + 1) / 2 + c) = kk == 0 ? a.z : (kk == 1 ? -a.y : a.x);
-        }
-    }
-}
-
 // One column of the contact-space matrix A = J M^-1 J^T, computed by one lane without barriers: the response of
 // the articulated system (inertias left in shared memory by the dynamics ABA) to a unit impulse along direction k
 // of contact j.  The impulse walks up the tree to the root (recording u = -S^T p per level in registers), the 6x6
@@ -1014,12 +962,9 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
     SC_STAGE {
         SC_LANE;
         const int nc = f2i(F(O_NC));
-#if !defined(SC_TWO_COLUMNS)
+        // (dealing the columns of all four samples over all 32 lanes was measured 13 % slower: lanes of one sample
+        // share 8 of the 32 banks, the tile's interleave only keeps different samples apart)
         for (int c = slot; c < 3 * nc; c += QUAD) contact_column(S, T, nc, c);
-#else
-        if (f2i(F(O_TM)) & TM_TWO_BODY) for (int c = slot; c < 3 * nc; c += QUAD) contact_column(S, T, nc, c);
-        else for (int c = slot; c < 3 * nc; c += QUAD) contact_column_ground(S, T, nc, c);
-#endif
     }
     SC_SYNC();
     SC_T(8);
