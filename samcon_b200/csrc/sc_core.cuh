@@ -26,7 +26,8 @@
 #if defined(__CUDACC__)
 #define SC_DEV __device__ __forceinline__
 // phase-level functions; measured on B200: making them real calls (__noinline__, 14.4k -> 13.1k SASS instructions)
-// was 3-5 % slower than inlining them into the step loop
+// was 3-5 % slower than inlining them into the step loop, also when only the ones with several call sites (fk_sweep,
+// aba) are shared
 #define SC_PHASE __device__ __forceinline__
 #define SC_CALL __device__ __noinline__
 #define SC_SYNC() __syncwarp()
@@ -34,6 +35,7 @@
 // the same code region, because the step loop is ~170 KB of SASS and 8 warps at 8 different places in it starve
 // on instruction fetch (ncu: stalled_no_instruction 7.7 per issue on the walk workload without it, 0.2 with the
 // warps aligned).  Every warp of the CTA must execute the same number of these, see rollout_tile().
+// (named barriers over groups of 5 / 2 warps instead of the whole CTA: 39.8 / 67 ms against 32.7 ms)
 #define SC_CTA_SYNC() __syncthreads()
 #ifndef SC_BAR_MASK
 #define SC_BAR_MASK 31
@@ -972,10 +974,11 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
     if (part == 1) {
     // ---- projected Gauss-Seidel, Bullet row order: all normals, then the friction pairs -------------------------
 #if defined(__CUDACC__)
-    if (ncmax <= 2) gs_registers<2>(sm, T);
-    else if (ncmax <= 4) gs_registers<4>(sm, T);
-    else if (ncmax <= 6) gs_registers<6>(sm, T);
-    else gs_registers<8>(sm, T);
+    // one sweep size for every warp: variants unrolled for 2 / 4 / 6 contacts do less work for tiles with few contacts,
+    // but put the CTA's warps into different code at the same time, and instruction fetch is what this kernel is short
+    // of (measured: 1 variant 32.4 ms, 4 variants 32.7 ms per walk window)
+    (void)ncmax;
+    gs_registers<MAXC>(sm, T);
     SC_T(9);
 #else
     SC_STAGE {
