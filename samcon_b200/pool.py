@@ -185,8 +185,15 @@ class GpuSamplePool:
             actions = np.asarray(actions, dtype=np.float32)
         st, cost, info = self.window(self._elites, actions, np.asarray(target_state, dtype=np.float32), nsteps)
         self._last = (st, cost, info)
-        return (st.cpu().numpy().astype(np.float64), cost.cpu().numpy().astype(np.float64),
-                info.cpu().numpy().astype(np.float64))
+        # device -> pinned host staging (allocated once per sample count), one synchronisation for the three results
+        S = st.shape[0]
+        if getattr(self, "_stage_S", None) != S:
+            self._stage = tuple(torch.empty(t.shape, dtype=torch.float32, pin_memory=True) for t in (st, cost, info))
+            self._stage_S = S
+        for h, d in zip(self._stage, (st, cost, info)):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return tuple(h.numpy().astype(np.float64) for h in self._stage)
 
     def select_last(self, nSave):
         """Trajectory.select('greedy') on the device for the window just simulated -> host int64 indices."""
