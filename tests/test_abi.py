@@ -53,3 +53,31 @@ def test_pool_refuses_without_gpu(character):
     from samcon_b200.pool import GpuSamplePool
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         GpuSamplePool(character, 0)
+
+
+def test_sc_create_validates_the_model_before_touching_cuda(lib_path, character):
+    """Error behaviour of the C ABI (no compute, works on a box without a GPU): a malformed model is refused with
+    SC_EINVAL and a message; every entry point refuses a null handle."""
+    from samcon_b200 import abi
+    lib = abi.load()
+    m, keep = abi.make_model(character)
+    h = C.c_void_p()
+    m.max_contacts = 99
+    rc = lib.sc_create(C.byref(h), C.byref(m), 0)
+    assert rc == -1 and b"max_contacts" in lib.sc_last_error(h)
+    assert lib.sc_destroy(h) == 0
+    m, keep = abi.make_model(character)
+    m.nlev = 1                                                    # level table no longer covers the 18 bodies
+    h = C.c_void_p()
+    assert lib.sc_create(C.byref(h), C.byref(m), 0) == -1 and len(lib.sc_last_error(h)) > 0
+    lib.sc_destroy(h)
+    m, keep = abi.make_model(character)
+    m.npair = 4000                                                # more primitive pairs than SC_MAX_PAIRS
+    h = C.c_void_p()
+    assert lib.sc_create(C.byref(h), C.byref(m), 0) == -1 and b"npair" in lib.sc_last_error(h)
+    lib.sc_destroy(h)
+    assert lib.sc_create(None, C.byref(m), 0) == -1
+    assert lib.sc_destroy(None) == -1 and lib.sc_launch_count(None) == 0
+    assert lib.sc_window(None, None, 1, None, 1, None, None, 1, None, 1, 1, None, None, None, None) == -1
+    assert lib.sc_select(None, None, None, 1, 1, None, None, None) == -1
+    assert lib.sc_last_error(None) == b"null handle"

@@ -154,3 +154,22 @@ def test_committed_fixture_windows(pool):
         st, cost, info = _run(pool, g[f"{key}_parents"], g[f"{key}_actions"], g[f"{key}_target"], int(g[f"{key}_nsteps"]), 1)
         assert joint_rms(st, g[f"{key}_state"]).max() < JOINT_TOL
         np.testing.assert_allclose(cost, g[f"{key}_cost"], rtol=COST_RTOL)
+
+
+def test_select_edge_cases(pool):
+    """Trajectory.select semantics at the edges: ties by index, NaN / inf costs last, a segment shorter than E padded
+    with -1 / +inf, E == n, one-element segments."""
+    import torch
+    c = torch.tensor([3.0, 1.0, float("nan"), 1.0, float("inf"), -2.0, 1.0, float("-inf")], device="cuda")
+    idx, ec = pool.select(c, 8)
+    assert idx[0].tolist() == [7, 5, 1, 3, 6, 0, 4, 2]
+    assert torch.isnan(ec[0, 7]) and ec[0, 6] == float("inf")
+    seg = torch.tensor([0, 3, 4, 8], dtype=torch.int32, device="cuda")
+    idx, ec = pool.select(c, 4, seg_offsets=seg)
+    assert idx.tolist() == [[1, 0, 2, -1], [3, -1, -1, -1], [7, 5, 6, 4]]
+    assert ec[0, 3] == float("inf") and ec[1, 1] == float("inf")
+    # bad arguments come back as errors, not launches
+    with pytest.raises(RuntimeError, match="sc_select"):
+        pool.select(c, 0)
+    with pytest.raises((RuntimeError, ValueError)):
+        pool.window(torch.zeros(3, 132, device="cuda"), torch.zeros(7, 68, device="cuda"), torch.zeros(132, device="cuda"), 1)
