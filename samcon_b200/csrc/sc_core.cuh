@@ -1,6 +1,6 @@
 // sc_core.cuh -- per-sample humanoid rollout, written as "lane stages".
 //
-// Mapping: one sample is owned by a group of QUAD = 8 lanes; a warp carries a TILE of 4 samples.
+// Mapping: one sample is owned by a group of LPS = 8 lanes; a warp carries a TILE of 4 samples.
 // lane = slot*4 + s  (s = sample in tile 0..3, slot = 0..7).  Bodies are numbered level by level and no tree
 // level is wider than 4, so in every tree sweep the group's lane `slot` owns body level_start[d]+slot.
 // All per-sample working data lives in shared memory, interleaved so that word w of sample s sits at
@@ -70,12 +70,12 @@ constexpr int MAXLEV = SC_MAX_LEVELS;
 constexpr int MAXC = SC_MAX_CONTACTS;
 constexpr int NR = 3 * MAXC;
 constexpr int TILE = 4;   // samples per warp
-constexpr int QUAD = 8;   // lanes per sample (the name predates the 8-lane mapping)
-static_assert(TILE * QUAD == 32, "one tile per warp");
+constexpr int LPS = 8;    // lanes per sample
+static_assert(TILE * LPS == 32, "one tile per warp");
 
 // self-collision tables (part of Tables, in shared memory)
 constexpr int NPRIM = SC_MAX_PRIMS, NPAIR = SC_MAX_PAIRS;
-constexpr int PAIRS_PER_LANE_MAX = (NPAIR + QUAD - 1) / QUAD, PRIMS_PER_LANE_MAX = (NPRIM + QUAD - 1) / QUAD;
+constexpr int PAIRS_PER_LANE_MAX = (NPAIR + LPS - 1) / LPS, PRIMS_PER_LANE_MAX = (NPRIM + LPS - 1) / LPS;
 struct SelfTables {
     int nprim, npair, prims_per_lane, pairs_per_lane;
     float prim[NPRIM * 8];              // sphere-swept segment in the body frame: p0, p1, radius, bounding radius about the midpoint
@@ -137,7 +137,7 @@ constexpr int O_END_DEV = O_LAM + NR;
 constexpr int O_AM = O_IC;                        // contact-space matrix, packed lower triangle (contact solve)
 constexpr int O_ZC = O_IC;                        // collide: signed distance per candidate (ground points, then pairs) ...
 constexpr int O_CNT = O_ZC + SC_MAX_CAND + NPAIR; // ... hits per lane (ground, pairs) ...
-constexpr int O_PCEN = O_CNT + 2 * QUAD;          // ... and world centres of the self-collision primitives (3)
+constexpr int O_PCEN = O_CNT + 2 * LPS;          // ... and world centres of the self-collision primitives (3)
 constexpr int HL_MAX = 32;                        // hits (distance, candidate) compacted over O_PCEN when more than maxc
 constexpr int O_HL = O_PCEN;
 static_assert(2 * HL_MAX <= 3 * NPRIM, "hit list must fit in PCEN");
@@ -557,7 +557,7 @@ SC_DEV int cb_b(int cb) { return (cb >> 8) - 1; }
 // that pass.  Stage 3: with the hit counts of the lower lanes as offset every lane appends its hits, so the contact
 // list is in candidate order (ground points, then pairs); only when more than `maxc` candidates are inside the
 // margin does lane 0 pick the deepest serially.
-constexpr int CAND_PER_LANE_MAX = (SC_MAX_CAND + QUAD - 1) / QUAD;
+constexpr int CAND_PER_LANE_MAX = (SC_MAX_CAND + LPS - 1) / LPS;
 constexpr float NO_HIT = 1.0e30f;
 
 SC_DEV float clamp01(float x) { return fminf(1.0f, fmaxf(0.0f, x)); }
@@ -687,15 +687,15 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
                 hits += dist < T.cthresh ? 1 : 0;
             }
         }
-        F(O_CNT + QUAD + slot) = i2f(hits);
+        F(O_CNT + LPS + slot) = i2f(hits);
     }
     SC_SYNC();
     SC_STAGE {
         SC_LANE;
         int ofs = 0, ofs2 = 0, total = 0;
 #pragma unroll
-        for (int l = 0; l < QUAD; l++) {
-            const int n = f2i(F(O_CNT + l)), n2 = f2i(F(O_CNT + QUAD + l));
+        for (int l = 0; l < LPS; l++) {
+            const int n = f2i(F(O_CNT + l)), n2 = f2i(F(O_CNT + LPS + l));
             ofs += l < slot ? n : 0;
             ofs2 += (l < slot ? n2 : 0) + n;
             total += n + n2;
@@ -717,7 +717,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
                         }
                     }
                 }
-            if (f2i(F(O_CNT + QUAD + slot)) > 0)
+            if (f2i(F(O_CNT + LPS + slot)) > 0)
                 for (int i = 0; i < ST.pairs_per_lane; i++) {
                     const int pr = slot * ST.pairs_per_lane + i;
                     if (pr < ST.npair) {
@@ -740,7 +740,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
         const int total = f2i(F(O_NC));
         unsigned keep = 0;
         if (total > T.maxc && total <= HL_MAX) {
-            for (int h = slot; h < total; h += QUAD) {
+            for (int h = slot; h < total; h += LPS) {
                 const float zh = F(O_HL + 2 * h);
                 int rank = 0;
                 for (int g = 0; g < total; g++) {
@@ -767,17 +767,17 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
             for (int j = 0; j < n; j++) write_contact(S, T, ST, j, f2i(F(O_CB + j)), F(O_CD + j));
         }
         F(O_CNT + slot) = i2f((int)keep);
-        if (slot == 0) F(O_CNT + QUAD) = i2f(total);      // O_NC is rewritten in the next stage while others still need the count
+        if (slot == 0) F(O_CNT + LPS) = i2f(total);      // O_NC is rewritten in the next stage while others still need the count
     }
     SC_SYNC();
     SC_STAGE {
         SC_LANE;
-        const int total = f2i(F(O_CNT + QUAD));
+        const int total = f2i(F(O_CNT + LPS));
         if (total > T.maxc && total <= HL_MAX) {
             unsigned keep = 0;
 #pragma unroll
-            for (int l = 0; l < QUAD; l++) keep |= (unsigned)f2i(F(O_CNT + l));
-            for (int h = slot; h < total; h += QUAD)
+            for (int l = 0; l < LPS; l++) keep |= (unsigned)f2i(F(O_CNT + l));
+            for (int h = slot; h < total; h += LPS)
                 if ((keep >> h) & 1u) {
 #if defined(__CUDA_ARCH__)
                     const int pos = __popc(keep & ((1u << h) - 1u));
@@ -869,7 +869,7 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
 }
 
 #if defined(__CUDACC__)
-// Device version of the Gauss-Seidel sweep.  Lane `slot` of a sample owns rows slot, slot+QUAD, ... of its contact
+// Device version of the Gauss-Seidel sweep.  Lane `slot` of a sample owns rows slot, slot+LPS, ... of its contact
 // system; those rows of the (symmetric) matrix, the residuals and the impulses stay in registers for all
 // iterations, the owner of the updated row broadcasts the impulse change to the sample's lanes with one shuffle,
 // and every lane folds it into its residuals.  Rows beyond 3*nc are zero rows and never move.  NCT = contacts the
@@ -880,11 +880,11 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
     float *S = sm + (lane & (TILE - 1));
     const int slot = lane / TILE;
     const int nr = 3 * f2i(F(O_NC));
-    constexpr int NRT = 3 * NCT, RPL = (NRT + QUAD - 1) / QUAD;     // rows per lane
+    constexpr int NRT = 3 * NCT, RPL = (NRT + LPS - 1) / LPS;     // rows per lane
     float a[RPL][NRT], res[RPL], lam[RPL], dgi[RPL], lamn[NCT], muc[NCT];
 #pragma unroll
     for (int m = 0; m < RPL; m++) {
-        const int row = slot + QUAD * m;
+        const int row = slot + LPS * m;
         const bool live = row < nr;
 #pragma unroll
         for (int c = 0; c < NRT; c++) {
@@ -906,7 +906,7 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
 #pragma unroll
                 for (int k = (pass ? 1 : 0); k < (pass ? 3 : 1); k++) {
                     constexpr int dummy = 0; (void)dummy;
-                    const int r = 3 * c + k, owner = r % QUAD, m = r / QUAD;
+                    const int r = 3 * c + k, owner = r % LPS, m = r / LPS;
                     float nl = lam[m] + res[m] * dgi[m];
                     const float lim = k == 0 ? 3.0e38f : muc[c] * lamn[c];
                     nl = fminf(lim, fmaxf(k == 0 ? 0.0f : -lim, nl));
@@ -921,7 +921,7 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
     }
 #pragma unroll
     for (int m = 0; m < RPL; m++) {
-        const int row = slot + QUAD * m;
+        const int row = slot + LPS * m;
         if (row < nr) F(O_LAM + row) = lam[m];
     }
     __syncwarp();
@@ -935,7 +935,7 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
     SC_STAGE {
         SC_LANE;
         const int nc = f2i(F(O_NC));
-        for (int j = slot; j < nc; j += QUAD) {
+        for (int j = slot; j < nc; j += LPS) {
             const int cb = f2i(F(O_CB + j)), ba = cb_a(cb), bb = cb_b(cb);
             V3 vp = ld3(S, O_TW + 6 * ba + 3) + cross(ld3(S, O_TW + 6 * ba), ld3(S, O_CR + 3 * j));
             if (bb >= 0) vp = vp - ld3(S, O_TW + 6 * bb + 3) - cross(ld3(S, O_TW + 6 * bb), ld3(S, O_CR2 + 3 * j));
@@ -946,7 +946,7 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
             F(O_RHS + 3 * j + 2) = -dot(fr.d[2], vp);
             F(O_LAM + 3 * j) = 0; F(O_LAM + 3 * j + 1) = 0; F(O_LAM + 3 * j + 2) = 0;
         }
-        if (slot == QUAD - 1) {
+        if (slot == LPS - 1) {
             int mask = 0;
             for (int j = 0; j < nc; j++) {
                 const int cb = f2i(F(O_CB + j));
@@ -966,7 +966,7 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
         const int nc = f2i(F(O_NC));
         // (dealing the columns of all four samples over all 32 lanes was measured 13 % slower: lanes of one sample
         // share 8 of the 32 banks, the tile's interleave only keeps different samples apart)
-        for (int c = slot; c < 3 * nc; c += QUAD) contact_column(S, T, nc, c);
+        for (int c = slot; c < 3 * nc; c += LPS) contact_column(S, T, nc, c);
     }
     SC_SYNC();
     SC_T(8);
@@ -984,7 +984,7 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
     SC_STAGE {
         SC_LANE;
         const int nc = f2i(F(O_NC));
-        for (int r = slot; r < 3 * nc; r += QUAD) {
+        for (int r = slot; r < 3 * nc; r += LPS) {
             F(O_DGI + r) = 1.0f / F(O_AM + r * (r + 1) / 2 + r);
             F(O_RES + r) = F(O_RHS + r);
         }
@@ -1004,7 +1004,7 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
             }
             const float dl = F(O_DEL + ((t + 1) & 1));
             if (rp >= 0 && dl != 0.0f)
-                for (int i = slot; i < 3 * nc; i += QUAD) {
+                for (int i = slot; i < 3 * nc; i += LPS) {
                     const int hi = i > rp ? i : rp, lo = i > rp ? rp : i;
                     F(O_RES + i) -= F(O_AM + hi * (hi + 1) / 2 + lo) * dl;
                 }
@@ -1015,7 +1015,7 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
                 if (c < nc) {
                     const int k = tl < ncmax ? 0 : 1 + ((tl - ncmax) & 1);
                     const int r = 3 * c + k;
-                    if ((r % QUAD) == slot) {
+                    if ((r % LPS) == slot) {
                         const float lam = F(O_LAM + r);
                         float nl = lam + F(O_RES + r) * F(O_DGI + r);
                         if (k == 0) nl = fmaxf(nl, 0.0f);
@@ -1123,7 +1123,7 @@ SC_PHASE void integrate(float *sm, const TT &T, int L0, int L1) {
     SC_STAGE {
         SC_LANE;
         const float mv = T.maxvel, h = T.h;
-        for (int b = slot; b < T.nb; b += QUAD) {
+        for (int b = slot; b < T.nb; b += LPS) {
             if (b == 0) {
 #pragma unroll
                 for (int i = 0; i < 6; i++) F(O_VB + i) = fminf(mv, fmaxf(-mv, F(O_VB + i)));
@@ -1162,12 +1162,12 @@ SC_DEV void load_state(float *sm, const TT &T, int L0, int L1, const float *rows
         int k = tile0 + (lane & (TILE - 1));
         if (k >= S_total) k = S_total - 1;   // padding lanes replay the last sample and never write
         const float *src = rows + (size_t)(parent_idx ? parent_idx[k] : k / children) * SC_STATE_DIM;
-        for (int i = slot; i < SC_STATE_DIM; i += QUAD) F(state_word(T, i)) = src[i];
+        for (int i = slot; i < SC_STATE_DIM; i += LPS) F(state_word(T, i)) = src[i];
     }
     SC_SYNC();
     SC_STAGE {
         SC_LANE;
-        for (int b = slot; b < T.nb; b += QUAD) {
+        for (int b = slot; b < T.nb; b += LPS) {
             const int o = O_Q + 4 * b;
             const float n = rsq(F(o) * F(o) + F(o + 1) * F(o + 1) + F(o + 2) * F(o + 2) + F(o + 3) * F(o + 3));
             F(o) *= n; F(o + 1) *= n; F(o + 2) *= n; F(o + 3) *= n;
@@ -1286,7 +1286,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             int k = tile0 + (lane & (TILE - 1));
             if (k >= a.S) k = a.S - 1;
             const float *act = a.actions + (size_t)k * (4 * T.nj);
-            for (int b = 1 + slot; b < T.nb; b += QUAD) pd_term_body(S, T, b, act);
+            for (int b = 1 + slot; b < T.nb; b += LPS) pd_term_body(S, T, b, act);
         }
         SC_SYNC();
         SC_T(2);
@@ -1333,9 +1333,9 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
         if (k < a.S) {
             if (a.out_state) {
                 float *dst = a.out_state + (size_t)k * SC_STATE_DIM;
-                for (int i = slot; i < SC_STATE_DIM; i += QUAD) dst[i] = F(state_word(T, i));
+                for (int i = slot; i < SC_STATE_DIM; i += LPS) dst[i] = F(state_word(T, i));
             }
-            if (a.out_feat) for (int i = slot; i < 18; i += QUAD) a.out_feat[(size_t)k * 18 + i] = F(O_FEAT + i);
+            if (a.out_feat) for (int i = slot; i < 18; i += LPS) a.out_feat[(size_t)k * 18 + i] = F(O_FEAT + i);
             if (slot == 0 && (a.out_cost || a.out_cost6)) {
                 const int q = a.sample_seq ? a.sample_seq[k] : 0;
                 float c[6];

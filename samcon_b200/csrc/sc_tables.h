@@ -48,7 +48,7 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
         for (int k = 0; k < 10; k++) { T->idyn[10 * b + k] = m->inertia_dyn[10 * b + k]; T->ipd[10 * b + k] = m->inertia_pd[10 * b + k]; }
         T->kp[b] = m->kp[b]; T->kd[b] = m->kd[b]; T->maxf[b] = m->maxf[b]; T->jw[b] = m->joint_weights[b];
     }
-    T->cand_per_lane = (m->ncand + QUAD - 1) / QUAD;
+    T->cand_per_lane = (m->ncand + LPS - 1) / LPS;
     for (int c = 0; c < m->ncand; c++) {
         if (m->cand_body[c] < 0 || m->cand_body[c] >= m->nb) SC_FAIL("bad cand_body");
         T->cand_body[c] = m->cand_body[c];
@@ -74,8 +74,8 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
     if (m->npair > 0) {
         if (m->nprim < 1 || m->nprim > NPRIM || !m->prim || !m->prim_body || !m->pair) SC_FAIL("nprim=%d outside 1..%d", m->nprim, NPRIM);
         ST->nprim = m->nprim; ST->npair = m->npair;
-        ST->prims_per_lane = (m->nprim + QUAD - 1) / QUAD;
-        ST->pairs_per_lane = (m->npair + QUAD - 1) / QUAD;
+        ST->prims_per_lane = (m->nprim + LPS - 1) / LPS;
+        ST->pairs_per_lane = (m->npair + LPS - 1) / LPS;
         for (int p = 0; p < m->nprim; p++) {
             if (m->prim_body[p] < 0 || m->prim_body[p] >= m->nb) SC_FAIL("bad prim_body");
             ST->prim_body[p] = (unsigned char)m->prim_body[p];
