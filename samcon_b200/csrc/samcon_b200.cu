@@ -102,8 +102,10 @@ __global__ void sc_sample_gen_kernel(const float *__restrict__ target, const flo
         const float lim = limits[3 * j + c];
         // uniform: U(-v, v) (samcon.py:113-118); gaussian: N(0, v) with v the variance (samcon.py:104-111)
         e[c] += gaussian ? u[c] * sqrtf(lim) : u[c] * 2.0f * lim - lim;
-        while (e[c] > PI) e[c] -= 2.0f * PI;       // samcon.py:130-133
-        while (e[c] < -PI) e[c] += 2.0f * PI;
+        // samcon.py:130-133 wraps with `while` loops; an atan2 output plus a cfg noise range needs at most two turns, and
+        // the bound keeps a non-finite input (inf limits / NaN target) from spinning the kernel
+        for (int it = 0; it < 4 && e[c] > PI; it++) e[c] -= 2.0f * PI;
+        for (int it = 0; it < 4 && e[c] < -PI; it++) e[c] += 2.0f * PI;
     }
     // intrinsic XYZ Euler -> quaternion = qx (x) qy (x) qz (scipy from_euler("XYZ").as_quat(), samcon.py:136-137)
     float sa, ca, sb, cb, sc_, cc;
