@@ -225,7 +225,10 @@ static int sc_fail(sc_context *h, int code, const char *fmt, ...) {
 }
 #define SC_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return sc_fail(h, SC_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
-constexpr int WPB = 10;   // warps (tiles of 4 samples) per CTA: 40 samples x 5.4 KB + tables fill the 227 KB of one SM
+#ifndef SC_WPB
+#define SC_WPB 10
+#endif
+constexpr int WPB = SC_WPB;   // warps (tiles of 4 samples) per CTA: 40 samples x 5.4 KB + tables fill the 227 KB of one SM
 
 extern "C" int sc_create(sc_handle *out, const sc_model *model, int device) {
     if (!out) return SC_EINVAL;

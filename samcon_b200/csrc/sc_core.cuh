@@ -69,8 +69,11 @@ constexpr int NB = SC_MAX_BODIES;
 constexpr int MAXLEV = SC_MAX_LEVELS;
 constexpr int MAXC = SC_MAX_CONTACTS;
 constexpr int NR = 3 * MAXC;
-constexpr int TILE = 4;   // samples per warp
-constexpr int LPS = 8;    // lanes per sample
+#ifndef SC_TILE
+#define SC_TILE 4
+#endif
+constexpr int TILE = SC_TILE;        // samples per warp
+constexpr int LPS = 32 / SC_TILE;    // lanes per sample
 static_assert(TILE * LPS == 32, "one tile per warp");
 
 // self-collision tables (part of Tables, in shared memory)
