@@ -459,6 +459,29 @@ static void seg_seg(const double *p1, const double *q1, const double *p2, const 
 static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
     static __thread oc_contact cand[MAXCAND];
     int n = 0;
+    /* link vs link first (candidate order = contact order = Gauss-Seidel row order: pairs, then ground points):
+     * one point per primitive pair, normal from the second link to the first */
+    for (int pi = 0; pi < m->npair; pi++) {
+        int sa = m->pair_a[pi], sb = m->pair_b[pi], la = m->sh_link[sa], lb = m->sh_link[sb];
+        double a0[3], a1[3], b0[3], b1[3], c1[3], c2[3], t[3], d[3];
+        mv3(k->R[la], m->cap_p0[sa], t); for (int a = 0; a < 3; a++) a0[a] = k->p[la][a] + t[a];
+        mv3(k->R[la], m->cap_p1[sa], t); for (int a = 0; a < 3; a++) a1[a] = k->p[la][a] + t[a];
+        mv3(k->R[lb], m->cap_p0[sb], t); for (int a = 0; a < 3; a++) b0[a] = k->p[lb][a] + t[a];
+        mv3(k->R[lb], m->cap_p1[sb], t); for (int a = 0; a < 3; a++) b1[a] = k->p[lb][a] + t[a];
+        seg_seg(a0, a1, b0, b1, c1, c2);
+        for (int a = 0; a < 3; a++) d[a] = c1[a] - c2[a];
+        double len = sqrt(dot3(d, d)), dist = len - m->cap_r[sa] - m->cap_r[sb];
+        if (dist < m->cthresh && len > 1e-9 && n < MAXCAND) {
+            oc_contact *cc = &cand[n++];
+            cc->link = la; cc->link2 = lb; cc->dist = dist; cc->mu = m->mu_self;
+            for (int a = 0; a < 3; a++) {
+                cc->n[a] = d[a] / len;
+                cc->pos[a] = c1[a] - m->cap_r[sa] * cc->n[a];
+                cc->pos2[a] = c2[a] + m->cap_r[sb] * cc->n[a];
+            }
+        }
+    }
+    /* ground */
     for (int s = 0; s < m->ns; s++) {
         int l = m->sh_link[s];
         double c[3], t[3];
@@ -483,27 +506,6 @@ static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
                 oc_contact *cc = &cand[n++];
                 cc->link = l; cc->link2 = -1; memcpy(cc->pos, pw, 24); memcpy(cc->pos2, pw, 24);
                 cc->n[0] = 0; cc->n[1] = 0; cc->n[2] = 1; cc->dist = pw[2]; cc->mu = m->mu;
-            }
-        }
-    }
-    /* link vs link: one point per primitive pair, normal from the second link to the first */
-    for (int pi = 0; pi < m->npair; pi++) {
-        int sa = m->pair_a[pi], sb = m->pair_b[pi], la = m->sh_link[sa], lb = m->sh_link[sb];
-        double a0[3], a1[3], b0[3], b1[3], c1[3], c2[3], t[3], d[3];
-        mv3(k->R[la], m->cap_p0[sa], t); for (int a = 0; a < 3; a++) a0[a] = k->p[la][a] + t[a];
-        mv3(k->R[la], m->cap_p1[sa], t); for (int a = 0; a < 3; a++) a1[a] = k->p[la][a] + t[a];
-        mv3(k->R[lb], m->cap_p0[sb], t); for (int a = 0; a < 3; a++) b0[a] = k->p[lb][a] + t[a];
-        mv3(k->R[lb], m->cap_p1[sb], t); for (int a = 0; a < 3; a++) b1[a] = k->p[lb][a] + t[a];
-        seg_seg(a0, a1, b0, b1, c1, c2);
-        for (int a = 0; a < 3; a++) d[a] = c1[a] - c2[a];
-        double len = sqrt(dot3(d, d)), dist = len - m->cap_r[sa] - m->cap_r[sb];
-        if (dist < m->cthresh && len > 1e-9 && n < MAXCAND) {
-            oc_contact *cc = &cand[n++];
-            cc->link = la; cc->link2 = lb; cc->dist = dist; cc->mu = m->mu_self;
-            for (int a = 0; a < 3; a++) {
-                cc->n[a] = d[a] / len;
-                cc->pos[a] = c1[a] - m->cap_r[sa] * cc->n[a];
-                cc->pos2[a] = c2[a] + m->cap_r[sb] * cc->n[a];
             }
         }
     }

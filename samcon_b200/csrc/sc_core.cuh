@@ -138,7 +138,7 @@ constexpr int O_RHS = O_TM + 1;
 constexpr int O_LAM = O_RHS + NR;
 constexpr int O_END_DEV = O_LAM + NR;
 constexpr int O_AM = O_IC;                        // contact-space matrix, packed lower triangle (contact solve)
-constexpr int O_ZC = O_IC;                        // collide: signed distance per candidate (ground points, then pairs) ...
+constexpr int O_ZC = O_IC;                        // collide: signed distance per candidate (pairs, then ground points) ...
 constexpr int O_CNT = O_ZC + SC_MAX_CAND + NPAIR; // ... hits per lane (ground, pairs) ...
 constexpr int O_PCEN = O_CNT + 2 * LPS;          // ... and world centres of the self-collision primitives (3)
 constexpr int HL_MAX = 32;                        // hits (distance, candidate) compacted over O_PCEN when more than maxc
@@ -558,7 +558,7 @@ SC_DEV int cb_b(int cb) { return (cb >> 8) - 1; }
 // Stage 1: the lanes of a sample test contiguous chunks of the ground candidates and place the self-collision
 // primitives' centres.  Stage 2: broad phase over the primitive pairs (bounding spheres), narrow phase for the few
 // that pass.  Stage 3: with the hit counts of the lower lanes as offset every lane appends its hits, so the contact
-// list is in candidate order (ground points, then pairs); only when more than `maxc` candidates are inside the
+// list is in candidate order (primitive pairs, then ground points); only when more than `maxc` candidates are inside the
 // margin does lane 0 pick the deepest serially.
 constexpr int CAND_PER_LANE_MAX = (SC_MAX_CAND + LPS - 1) / LPS;
 constexpr float NO_HIT = 1.0e30f;
@@ -605,18 +605,20 @@ SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, V3 &pa, V
     return true;
 }
 
-// u = unified candidate index: ground point u < ncand, else primitive pair u - ncand
+// u = unified candidate index: primitive pair u < npair, else ground point u - npair.  Link-vs-link contacts come first in
+// the contact list: a column only evaluates the rows at or after its own contact, so the (few) two-body columns pay for
+// the two-body rows and the ground columns never walk to a second body.
 SC_DEV void write_contact(float *S, const Tables &T, const SelfTables &ST, int j, int u, float z) {
-    if (u < T.ncand) {
-        const int b = T.cand_body[u];
-        const float *pt = T.cand + 4 * u;
+    if (u >= ST.npair) {
+        const int c = u - ST.npair, b = T.cand_body[c];
+        const float *pt = T.cand + 4 * c;
         F(O_CB + j) = i2f(b);
         const V3 o = mul(ldM(S, O_RW + 9 * b), mk(pt[0], pt[1], pt[2]));      // lowest point of the sphere: centre - r ez
         F(O_CR + 3 * j) = o.x;
         F(O_CR + 3 * j + 1) = o.y;
         F(O_CR + 3 * j + 2) = o.z - pt[3];
     } else {
-        const int pr = u - T.ncand;
+        const int pr = u;
         const int ba = ST.prim_body[ST.pair_a[pr]], bb = ST.prim_body[ST.pair_b[pr]];
         V3 pa, pb, n;
         float d;
@@ -643,7 +645,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
                 const float *pt = T.cand + 4 * c;
                 const float z = F(O_PW + 3 * b + 2) + F(O_RW + 9 * b + 6) * pt[0] + F(O_RW + 9 * b + 7) * pt[1] +
                                 F(O_RW + 9 * b + 8) * pt[2] - pt[3];
-                F(O_ZC + c) = z;
+                F(O_ZC + ST.npair + c) = z;
                 hits += z < T.cthresh ? 1 : 0;
             }
         }
@@ -672,7 +674,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
             if (i < ST.pairs_per_lane && pr < ST.npair) {
                 const V3 d = ld3(S, O_PCEN + 3 * ST.pair_a[pr]) - ld3(S, O_PCEN + 3 * ST.pair_b[pr]);
                 near |= (dot(d, d) < ST.pair_r2[pr] ? 1u : 0u) << i;
-                F(O_ZC + T.ncand + pr) = NO_HIT;
+                F(O_ZC + pr) = NO_HIT;
             }
         }
         while (near) {
@@ -686,7 +688,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
             V3 pa, pb, n;
             float dist;
             if (pair_contact(S, ST, pr, pa, pb, n, dist)) {
-                F(O_ZC + T.ncand + pr) = dist;
+                F(O_ZC + pr) = dist;
                 hits += dist < T.cthresh ? 1 : 0;
             }
         }
@@ -695,12 +697,12 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
     SC_SYNC();
     SC_STAGE {
         SC_LANE;
-        int ofs = 0, ofs2 = 0, total = 0;
+        int ofs = 0, ofs2 = 0, total = 0;        // ofs: this lane's first ground slot, ofs2: its first pair slot
 #pragma unroll
         for (int l = 0; l < LPS; l++) {
             const int n = f2i(F(O_CNT + l)), n2 = f2i(F(O_CNT + LPS + l));
-            ofs += l < slot ? n : 0;
-            ofs2 += (l < slot ? n2 : 0) + n;
+            ofs += (l < slot ? n : 0) + n2;
+            ofs2 += l < slot ? n2 : 0;
             total += n + n2;
         }
 #if defined(SC_PROFILE) && defined(__CUDACC__)
@@ -709,25 +711,25 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
 #endif
         const bool list = total > T.maxc && total <= HL_MAX;   // too many: compact (z, u) first, pick in parallel below
         if (total <= T.maxc || list) {
-            if (f2i(F(O_CNT + slot)) > 0)
-                for (int i = 0; i < T.cand_per_lane; i++) {
-                    const int c = slot * T.cand_per_lane + i;
-                    if (c < T.ncand) {
-                        const float z = F(O_ZC + c);
-                        if (z < T.cthresh) {
-                            if (list) { F(O_HL + 2 * ofs) = z; F(O_HL + 2 * ofs + 1) = i2f(c); ofs++; }
-                            else write_contact(S, T, ST, ofs++, c, z);
-                        }
-                    }
-                }
             if (f2i(F(O_CNT + LPS + slot)) > 0)
                 for (int i = 0; i < ST.pairs_per_lane; i++) {
                     const int pr = slot * ST.pairs_per_lane + i;
                     if (pr < ST.npair) {
-                        const float z = F(O_ZC + T.ncand + pr);
+                        const float z = F(O_ZC + pr);
                         if (z < T.cthresh) {
-                            if (list) { F(O_HL + 2 * ofs2) = z; F(O_HL + 2 * ofs2 + 1) = i2f(T.ncand + pr); ofs2++; }
-                            else write_contact(S, T, ST, ofs2++, T.ncand + pr, z);
+                            if (list) { F(O_HL + 2 * ofs2) = z; F(O_HL + 2 * ofs2 + 1) = i2f(pr); ofs2++; }
+                            else write_contact(S, T, ST, ofs2++, pr, z);
+                        }
+                    }
+                }
+            if (f2i(F(O_CNT + slot)) > 0)
+                for (int i = 0; i < T.cand_per_lane; i++) {
+                    const int c = slot * T.cand_per_lane + i;
+                    if (c < T.ncand) {
+                        const float z = F(O_ZC + ST.npair + c);
+                        if (z < T.cthresh) {
+                            if (list) { F(O_HL + 2 * ofs) = z; F(O_HL + 2 * ofs + 1) = i2f(ST.npair + c); ofs++; }
+                            else write_contact(S, T, ST, ofs++, ST.npair + c, z);
                         }
                     }
                 }
