@@ -859,15 +859,21 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
                 const V3 ap = al + cross(aw, ld3(S, (s2 ? O_CR2 : O_CR) + 3 * i));
                 a = s2 ? a - ap : ap;
             }
-            const Frame fi = contact_frame_of(S, i, cbi);
-#pragma unroll
-            for (int kk = 0; kk < 3; kk++) {
-                const int rr = 3 * i + kk;
-                if (rr >= c) {
-                    const float v = dot(fi.d[kk], a);
-                    const int o = O_AM + rr * (rr + 1) / 2 + c;
-                    if (side) F(o) += v; else F(o) = v;
-                }
+            // projections on contact i's frame; a ground contact's frame is +z, -y, +x: components, no arithmetic
+            V3 pr = mk(a.z, -a.y, a.x);
+            if (cbi >> 8) {
+                const Frame fi = contact_frame(ld3(S, O_CN + 3 * i));
+                pr = mk(dot(fi.d[0], a), dot(fi.d[1], a), dot(fi.d[2], a));
+            }
+            const int r0 = 3 * i, o0 = O_AM + r0 * (r0 + 1) / 2 + c;
+            if (side) {
+                if (r0 >= c) F(o0) += pr.x;
+                if (r0 + 1 >= c) F(o0 + r0 + 1) += pr.y;
+                if (r0 + 2 >= c) F(o0 + 2 * r0 + 3) += pr.z;
+            } else {
+                if (r0 >= c) F(o0) = pr.x;
+                if (r0 + 1 >= c) F(o0 + r0 + 1) = pr.y;
+                if (r0 + 2 >= c) F(o0 + 2 * r0 + 3) = pr.z;
             }
         }
     }
