@@ -413,10 +413,14 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b, const bool PD) {
 #pragma unroll
         for (int i = 0; i < 6; i++) F(O_PC + i) = x[i];
         if (!PD) {
-            // base velocity update: w += h alpha ; v += h (a + w x v + g)   (spatial -> classical acceleration)
+            // base velocity update: w += h alpha ; v += h (a + w x v + g)   (spatial -> classical acceleration).
+            // The change of the body twist is handed to the children (O_IC slot, free in the outward sweep), so that
+            // the sweep leaves O_TW at the new velocities and no separate velocity pass is needed before the contacts.
             const V3 a = mk(x[3], x[4], x[5]) + cross(w, v);
-            F(O_VB) += T.h * x[0]; F(O_VB + 1) += T.h * x[1]; F(O_VB + 2) += T.h * x[2];
-            F(O_VB + 3) += T.h * (a.x + T.g[0]); F(O_VB + 4) += T.h * (a.y + T.g[1]); F(O_VB + 5) += T.h * (a.z + T.g[2]);
+            const V3 dw = T.h * mk(x[0], x[1], x[2]), dv = T.h * mk(a.x + T.g[0], a.y + T.g[1], a.z + T.g[2]);
+            st3(S, O_VB, ld3(S, O_VB) + dw); st3(S, O_VB + 3, ld3(S, O_VB + 3) + dv);
+            st3(S, O_TW, w + dw); st3(S, O_TW + 3, v + dv);
+            st3(S, O_IC + 21 * T.icslot[0], dw); st3(S, O_IC + 21 * T.icslot[0] + 3, dv);
         }
         return;
     }
@@ -478,6 +482,12 @@ SC_DEV void aba_forward_body(float *S, const Tables &T, int b, const bool PD) {
         st3(S, O_TAU + 3 * b, mk(fminf(mf, fmaxf(-mf, t.x)), fminf(mf, fmaxf(-mf, t.y)), fminf(mf, fmaxf(-mf, t.z))));
     } else {
         st3(S, O_W + 3 * b, ld3(S, O_W + 3 * b) + T.h * qc);
+        // twist at the new velocities, same orientation: d omega_b = d omega_p + h qdd, d v_b = d v_p + d omega_p x r
+        const int op = O_IC + 21 * T.icslot[p], ob = O_IC + 21 * T.icslot[b];
+        const V3 dwp = ld3(S, op), dvp = ld3(S, op + 3);
+        const V3 dw = dwp + T.h * qdd, dv = dvp + cross(dwp, r);
+        st3(S, ob, dw); st3(S, ob + 3, dv);
+        st3(S, O_TW + 6 * b, w + dw); st3(S, O_TW + 6 * b + 3, v + dv);
     }
 }
 
@@ -1321,11 +1331,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
 #endif
             SC_BAR(64);
             SC_T(26);
-            if (ncmax > 0) {
-                fk_sweep(sm, T, L0, L1, false);
-                SC_T(6);
-                contact_solve(sm, T, L0, L1, ncmax, 0 SC_PROF_PASS);
-            }
+            if (ncmax > 0) contact_solve(sm, T, L0, L1, ncmax, 0 SC_PROF_PASS);      // O_TW is current: the ABA updated it
             SC_BAR(16);
             SC_T(27);
             if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 1 SC_PROF_PASS); SC_T(9); }
