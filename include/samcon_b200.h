@@ -23,7 +23,7 @@ extern "C" {
 #define SC_STATE_DIM 132  /* /root/reference/envs/humanoid_stable_pd.py:137-165 */
 #define SC_MAX_BODIES 18  /* moving bodies after folding fixed joints */
 #define SC_MAX_LEVELS 8
-#define SC_MAX_CAND 96    /* ground-contact candidate points */
+#define SC_MAX_CAND 80    /* ground-contact candidate points */
 #define SC_MAX_CPOINTS 24 /* cost points = URDF links */
 #define SC_MAX_CONTACTS 8 /* per-sample cap, deepest first */
 #define SC_MAX_PRIMS 24   /* self-collision primitives (sphere-swept segments) */
