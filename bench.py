@@ -307,7 +307,7 @@ def run_ours(args):
                        "walk_yml_window_s_at_nSample_2000": walk_window_s},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": S * 68 * 4 + 132 * 4,
-                    "d2h_bytes_per_step": S * (132 + 1 + 5) * 4 + E * 8},
+                    "d2h_bytes_per_step": S * (132 + 1 + 5) * 8 + E * 4},     # float64 results (widened on the device), int32 elite ids
             "roofline": roofline}
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
