@@ -431,16 +431,26 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b, const bool PD) {
     const V3 wj = ld3(S, O_WJ + 3 * b);
     const V3 cw = cross(w, wj), cv = cross(v, wj);
     stS(S, O_UA + 6 * b, A); stM(S, O_UB + 9 * b, B); stS(S, O_DI + 6 * b, K); st3(S, O_UU + 3 * b, u);
-    const M3 Am = tom(A), Km = tom(K);
-    const M3 AK = mul(Am, Km), BK = mul(B, Km);
-    const M3 AKA = mul(AK, Am), BKA = mul(BK, Am), BKB = mulBt(BK, B);
-    M3 Aa, Ba, Ca;
-    const M3 Cm = tom(C);
+    // Articulated inertia seen by the parent, IA - IA S (S^T IA S + arm)^-1 S^T IA with S = [1; 0] and K = (A + arm 1)^-1.
+    // K commutes with A and A K = 1 - arm K, so with P = arm K:
+    //   Aa = A - A K A = arm (1 - P),   Ba = B - B K A = arm B K,   Ca = C - B K B^T,   A K u = u - P u
+    // (arm = 0, the dynamics pass: a spherical joint passes no moment but its torque -- Aa = Ba = 0).
+    const M3 BK = mul(B, tom(K));
+    const S3 P = {arm * K.xx, arm * K.xy, arm * K.xz, arm * K.yy, arm * K.yz, arm * K.zz};
+    const S3 Aas = {arm - arm * P.xx, -arm * P.xy, -arm * P.xz, arm - arm * P.yy, -arm * P.yz, arm - arm * P.zz};
+    const M3 Aa = tom(Aas);
+    M3 Ba, Ca;
 #pragma unroll
-    for (int i = 0; i < 9; i++) { Aa.a[i] = Am.a[i] - AKA.a[i]; Ba.a[i] = B.a[i] - BKA.a[i]; Ca.a[i] = Cm.a[i] - BKB.a[i]; }
-    const V3 Ku = mul(K, u);
-    const V3 pan = pn + mul(Aa, cw) + mulT(Ba, cv) + mul(A, Ku);
-    const V3 paf = pf + mul(Ba, cw) + mul(Ca, cv) + mul(B, Ku);
+    for (int i = 0; i < 9; i++) Ba.a[i] = arm * BK.a[i];
+    {
+        // Ca = C - BK B^T is symmetric: six dot products
+        const float c00 = dot(row(BK, 0), row(B, 0)), c01 = dot(row(BK, 0), row(B, 1)), c02 = dot(row(BK, 0), row(B, 2));
+        const float c11 = dot(row(BK, 1), row(B, 1)), c12 = dot(row(BK, 1), row(B, 2)), c22 = dot(row(BK, 2), row(B, 2));
+        const S3 Cs = {C.xx - c00, C.xy - c01, C.xz - c02, C.yy - c11, C.yz - c12, C.zz - c22};
+        Ca = tom(Cs);
+    }
+    const V3 pan = pn + mul(Aas, cw) + mulT(Ba, cv) + (u - mul(P, u));
+    const V3 paf = pf + mul(Ba, cw) + mul(Ca, cv) + mul(BK, u);
     // shift the reference point to the parent's origin (r = p_b - p_parent); axes are shared, nothing to rotate
     const V3 r = ld3(S, O_RJ + 3 * b);
     M3 CR, Bp, Ap;
@@ -469,9 +479,11 @@ SC_DEV void aba_forward_body(float *S, const Tables &T, int b, const bool PD) {
     const V3 w = ld3(S, O_TW + 6 * b), v = ld3(S, O_TW + 6 * b + 3), wj = ld3(S, O_WJ + 3 * b);
     const V3 aw = alp + cross(w, wj);
     const V3 al = ap + cross(alp, r) + cross(v, wj);
-    const S3 A = ldS(S, O_UA + 6 * b), K = ldS(S, O_DI + 6 * b);
+    const S3 K = ldS(S, O_DI + 6 * b);
     const M3 B = ldM(S, O_UB + 9 * b);
-    const V3 qdd = mul(K, ld3(S, O_UU + 3 * b) - mul(A, aw) - mulT(B, al));
+    V3 qdd;
+    if (PD) qdd = mul(K, ld3(S, O_UU + 3 * b) - mul(ldS(S, O_UA + 6 * b), aw) - mulT(B, al));
+    else qdd = mul(K, ld3(S, O_UU + 3 * b) - mulT(B, al)) - aw;      // no armature: K A = 1, aw + qdd = K (u - B^T al)
     st3(S, O_PC + 6 * b, aw + qdd);
     st3(S, O_PC + 6 * b + 3, al);
     const V3 qc = mulT(ldM(S, O_RW + 9 * b), qdd);        // joint acceleration in child-frame coordinates
@@ -830,11 +842,11 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
             u[d] = mk(0, 0, 0);
             if (d <= dj) {
                 const int b = T.anc[bj][d];
+                // the contact phases see the dynamics pass's inertias (no armature): K A = 1, a spherical joint passes
+                // no moment, so pn + A K u = pn + u = 0 and only the force part goes on to the parent
                 u[d] = neg(pn);
-                const V3 Ku = mul(ldS(S, O_DI + 6 * b), u[d]);
-                pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
-                pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
-                pn = pn + cross(ld3(S, O_RJ + 3 * b), pf);
+                pf = pf + mul(ldM(S, O_UB + 9 * b), mul(ldS(S, O_DI + 6 * b), u[d]));
+                pn = cross(ld3(S, O_RJ + 3 * b), pf);
             }
         }
         float L[21], x[6] = {-pn.x, -pn.y, -pn.z, -pf.x, -pf.y, -pf.z};
@@ -860,8 +872,7 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
                             const int b = T.anc[bi][d];
                             al = al + cross(aw, ld3(S, O_RJ + 3 * b));
                             const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);
-                            const V3 qdd = mul(ldS(S, O_DI + 6 * b), uu - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
-                            aw = aw + qdd;
+                            aw = mul(ldS(S, O_DI + 6 * b), uu - mulT(ldM(S, O_UB + 9 * b), al));   // aw + K (uu - A aw - B^T al), K A = 1
                         }
                     }
                     if (!s2) { bprev = bi; awc = aw; alc = al; }
@@ -1087,10 +1098,8 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
                 } else {
                     const V3 u = neg(pn);
                     st3(S, O_UU + 3 * b, u);
-                    const V3 Ku = mul(ldS(S, O_DI + 6 * b), u);
-                    pn = pn + mul(ldS(S, O_UA + 6 * b), Ku);
-                    pf = pf + mul(ldM(S, O_UB + 9 * b), Ku);
-                    st3(S, O_PC + 6 * b, pn + cross(ld3(S, O_RJ + 3 * b), pf));
+                    pf = pf + mul(ldM(S, O_UB + 9 * b), mul(ldS(S, O_DI + 6 * b), u));            // pn + A K u = 0 (K A = 1)
+                    st3(S, O_PC + 6 * b, cross(ld3(S, O_RJ + 3 * b), pf));
                     st3(S, O_PC + 6 * b + 3, pf);
                 }
             }
@@ -1107,10 +1116,10 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
                 const V3 aw = ld3(S, O_PC + 6 * p), al = ld3(S, O_PC + 6 * p + 3) + cross(aw, ld3(S, O_RJ + 3 * b));
                 V3 u = mk(0, 0, 0);
                 if ((mask >> b) & 1) u = ld3(S, O_UU + 3 * b);
-                const V3 qdd = mul(ldS(S, O_DI + 6 * b), u - mul(ldS(S, O_UA + 6 * b), aw) - mulT(ldM(S, O_UB + 9 * b), al));
-                st3(S, O_PC + 6 * b, aw + qdd);
+                const V3 awn = mul(ldS(S, O_DI + 6 * b), u - mulT(ldM(S, O_UB + 9 * b), al));    // aw + K (u - A aw - B^T al), K A = 1
+                st3(S, O_PC + 6 * b, awn);
                 st3(S, O_PC + 6 * b + 3, al);
-                st3(S, O_W + 3 * b, ld3(S, O_W + 3 * b) + mulT(ldM(S, O_RW + 9 * b), qdd));
+                st3(S, O_W + 3 * b, ld3(S, O_W + 3 * b) + mulT(ldM(S, O_RW + 9 * b), awn - aw));
             }
         }
         SC_SYNC();
