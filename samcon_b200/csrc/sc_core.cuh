@@ -436,12 +436,7 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b, const bool PD) {
     //   Aa = A - A K A = arm (1 - P),   Ba = B - B K A = arm B K,   Ca = C - B K B^T,   A K u = u - P u
     // (arm = 0, the dynamics pass: a spherical joint passes no moment but its torque -- Aa = Ba = 0).
     const M3 BK = mul(B, tom(K));
-    const S3 P = {arm * K.xx, arm * K.xy, arm * K.xz, arm * K.yy, arm * K.yz, arm * K.zz};
-    const S3 Aas = {arm - arm * P.xx, -arm * P.xy, -arm * P.xz, arm - arm * P.yy, -arm * P.yz, arm - arm * P.zz};
-    const M3 Aa = tom(Aas);
-    M3 Ba, Ca;
-#pragma unroll
-    for (int i = 0; i < 9; i++) Ba.a[i] = arm * BK.a[i];
+    M3 Ca;
     {
         // Ca = C - BK B^T is symmetric: six dot products
         const float c00 = dot(row(BK, 0), row(B, 0)), c01 = dot(row(BK, 0), row(B, 1)), c02 = dot(row(BK, 0), row(B, 2));
@@ -449,23 +444,38 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b, const bool PD) {
         const S3 Cs = {C.xx - c00, C.xy - c01, C.xz - c02, C.yy - c11, C.yz - c12, C.zz - c22};
         Ca = tom(Cs);
     }
-    const V3 pan = pn + mul(Aas, cw) + mulT(Ba, cv) + (u - mul(P, u));
-    const V3 paf = pf + mul(Ba, cw) + mul(Ca, cv) + mul(BK, u);
-    // shift the reference point to the parent's origin (r = p_b - p_parent); axes are shared, nothing to rotate
+    // shift of the reference point to the parent's origin (r = p_b - p_parent); axes are shared, nothing to rotate:
+    // Bp = Ba - Ca rx,  Ap = Aa - Ba^T rx + rx Ba - rx Ca rx = Aa - Ba^T rx + rx Bp
     const V3 r = ld3(S, O_RJ + 3 * b);
-    M3 CR, Bp, Ap;
+    M3 CR, Bp, Ap, RB;
 #pragma unroll
     for (int i = 0; i < 3; i++) setrow(CR, i, cross(row(Ca, i), r));              // Ca * rx
+    V3 pan, paf = pf + mul(Ca, cv) + mul(BK, u);
+    if (PD) {
+        const S3 P = {arm * K.xx, arm * K.xy, arm * K.xz, arm * K.yy, arm * K.yz, arm * K.zz};
+        const S3 Aas = {arm - arm * P.xx, -arm * P.xy, -arm * P.xz, arm - arm * P.yy, -arm * P.yz, arm - arm * P.zz};
+        const M3 Aa = tom(Aas);
+        M3 Ba, BtR;
 #pragma unroll
-    for (int i = 0; i < 9; i++) Bp.a[i] = Ba.a[i] - CR.a[i];
-    // Ap = Aa - Ba^T rx + rx Ba - rx Ca rx = Aa - Ba^T rx + rx Bp
-    M3 BtR, RB;
+        for (int i = 0; i < 9; i++) Ba.a[i] = arm * BK.a[i];
+        pan = pn + mul(Aas, cw) + mulT(Ba, cv) + (u - mul(P, u));
+        paf = paf + mul(Ba, cw);
 #pragma unroll
-    for (int i = 0; i < 3; i++) setrow(BtR, i, cross(col(Ba, i), r));             // Ba^T * rx
+        for (int i = 0; i < 9; i++) Bp.a[i] = Ba.a[i] - CR.a[i];
 #pragma unroll
-    for (int j = 0; j < 3; j++) setcol(RB, j, cross(r, col(Bp, j)));              // rx * Bp
+        for (int i = 0; i < 3; i++) setrow(BtR, i, cross(col(Ba, i), r));         // Ba^T * rx
 #pragma unroll
-    for (int i = 0; i < 9; i++) Ap.a[i] = Aa.a[i] - BtR.a[i] + RB.a[i];
+        for (int j = 0; j < 3; j++) setcol(RB, j, cross(r, col(Bp, j)));          // rx * Bp
+#pragma unroll
+        for (int i = 0; i < 9; i++) Ap.a[i] = Aa.a[i] - BtR.a[i] + RB.a[i];
+    } else {
+        // no armature: Aa = Ba = 0, the joint passes on its torque and nothing else of the moment
+        pan = pn + u;
+#pragma unroll
+        for (int i = 0; i < 9; i++) Bp.a[i] = -CR.a[i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) setcol(Ap, j, cross(r, col(Bp, j)));          // rx * Bp
+    }
     const int o = O_IC + 21 * T.icslot[b];
     stS(S, o, upper(Ap)); stM(S, o + 6, Bp); stS(S, o + 15, upper(Ca));
     st3(S, O_PC + 6 * b, pan + cross(r, paf));
