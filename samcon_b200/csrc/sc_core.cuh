@@ -1008,7 +1008,12 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
         const int nc = f2i(F(O_NC));
         // (dealing the columns of all four samples over all 32 lanes was measured 13 % slower: lanes of one sample
         // share 8 of the 32 banks, the tile's interleave only keeps different samples apart)
-        for (int c = slot; c < 3 * nc; c += LPS) contact_column(S, T, nc, c);
+        // columns slot, 15 - slot, 16 + slot: a column evaluates the rows at or after its own, so pairing an early column
+        // with a late one evens out the lanes (8 contacts: 13-14 contact rows per lane instead of 10-17)
+        for (int m = 0; m < (3 * MAXC + LPS - 1) / LPS; m++) {
+            const int c = m == 1 ? 2 * LPS - 1 - slot : slot + LPS * m;
+            if (c < 3 * nc) contact_column(S, T, nc, c);
+        }
     }
     SC_SYNC();
     SC_T(8);
