@@ -911,22 +911,28 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
 }
 
 #if defined(__CUDACC__)
-// Device version of the Gauss-Seidel sweep.  Lane `slot` of a sample owns rows slot, slot+LPS, ... of its contact
-// system; those rows of the (symmetric) matrix, the residuals and the impulses stay in registers for all
-// iterations, the owner of the updated row broadcasts the impulse change to the sample's lanes with one shuffle,
-// and every lane folds it into its residuals.  Rows beyond 3*nc are zero rows and never move.  NCT = contacts the
-// sweep is unrolled for (>= the tile's largest count), so the control flow is uniform and branch free.
+// Device version of the Gauss-Seidel sweep.  The sweep visits the rows in Bullet's order (all normals, then the friction
+// pairs): position s = 0..3*NCT-1 is row gs_row(s).  Lane `slot` of a sample owns the three consecutive positions
+// 3*slot .. 3*slot+2; those rows of the (symmetric) matrix, their residuals and impulses stay in registers for all
+// iterations, the owner of the updated row broadcasts the impulse change to the sample's lanes with one shuffle, and
+// every lane folds it into its residuals.  Inside a lane's run of three the next row does not wait for that shuffle:
+// the owner already knows its own change, so the residual its next row needs is formed from the local value
+// (identical bits), and the broadcast only has to arrive before the next lane's run.  Rows beyond 3*nc are zero rows
+// and never move.  The sweep is unrolled for NCT contacts, so the control flow is uniform and branch free.
+__host__ __device__ constexpr int gs_row(int s, int nct) { return s < nct ? 3 * s : 3 * ((s - nct) / 2) + 1 + ((s - nct) & 1); }
+
 template <int NCT, class TT>
 __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
     const int lane = threadIdx.x & 31;
     float *S = sm + (lane & (TILE - 1));
     const int slot = lane / TILE;
     const int nr = 3 * f2i(F(O_NC));
-    constexpr int NRT = 3 * NCT, RPL = (NRT + LPS - 1) / LPS;     // rows per lane
+    constexpr int NRT = 3 * NCT, RPL = 3;                           // rows per lane: one run of the sweep
+    static_assert(NRT == RPL * LPS, "one run of three sweep positions per lane");
     float a[RPL][NRT], res[RPL], lam[RPL], dgi[RPL], lamn[NCT], muc[NCT];
 #pragma unroll
     for (int m = 0; m < RPL; m++) {
-        const int row = slot + LPS * m;
+        const int row = gs_row(RPL * slot + m, NCT);
         const bool live = row < nr;
 #pragma unroll
         for (int c = 0; c < NRT; c++) {
@@ -941,29 +947,28 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
     for (int c = 0; c < NCT; c++) { lamn[c] = 0.0f; muc[c] = (f2i(F(O_CB + c)) >> 8) ? T.mu_self : T.mu; }
     const int src0 = lane & (TILE - 1);
     for (int it = 0; it < T.niter; it++) {
+        float spec = 0.0f;
 #pragma unroll
-        for (int pass = 0; pass < 2; pass++)
+        for (int s = 0; s < NRT; s++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int r = gs_row(s, NCT), c = r / 3, k = r - 3 * c, owner = s / RPL, m = s % RPL;
+            // the owner's residual of this row: inside a run, the value formed from its own previous change
+            const float rcur = m > 0 ? spec : res[m];
+            float nl = lam[m] + rcur * dgi[m];
+            const float lim = k == 0 ? 3.0e38f : muc[c] * lamn[c];
+            nl = fminf(lim, fmaxf(k == 0 ? 0.0f : -lim, nl));
+            const float dloc = slot == owner ? nl - lam[m] : 0.0f;
+            if (slot == owner) lam[m] = nl;
+            if (m + 1 < RPL) spec = res[m + 1] - a[m + 1][r] * dloc;
+            const float d = __shfl_sync(0xffffffffu, dloc, src0 + TILE * owner);
+            if (k == 0) lamn[c] += d;
 #pragma unroll
-            for (int c = 0; c < NCT; c++) {
-#pragma unroll
-                for (int k = (pass ? 1 : 0); k < (pass ? 3 : 1); k++) {
-                    constexpr int dummy = 0; (void)dummy;
-                    const int r = 3 * c + k, owner = r % LPS, m = r / LPS;
-                    float nl = lam[m] + res[m] * dgi[m];
-                    const float lim = k == 0 ? 3.0e38f : muc[c] * lamn[c];
-                    nl = fminf(lim, fmaxf(k == 0 ? 0.0f : -lim, nl));
-                    float d = slot == owner ? nl - lam[m] : 0.0f;
-                    if (slot == owner) lam[m] = nl;
-                    d = __shfl_sync(0xffffffffu, d, src0 + TILE * owner);
-                    if (k == 0) lamn[c] += d;
-#pragma unroll
-                    for (int mm = 0; mm < RPL; mm++) res[mm] -= a[mm][r] * d;
-                }
-            }
+            for (int mm = 0; mm < RPL; mm++) res[mm] -= a[mm][r] * d;
+        }
     }
 #pragma unroll
     for (int m = 0; m < RPL; m++) {
-        const int row = slot + LPS * m;
+        const int row = gs_row(RPL * slot + m, NCT);
         if (row < nr) F(O_LAM + row) = lam[m];
     }
     __syncwarp();
