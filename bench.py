@@ -37,8 +37,8 @@ BYTES_PER_SAMPLE_STEP = 21.0
 METRIC, UNIT = "humanoid sample-sim-steps/sec", "sample-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload (S = 10 000, 100 steps), from the
 # committed `ncu --set full` capture; below the algorithmic 21 MB because one window's buffers sit in the 126 MB L2
-NCU_DRAM_BYTES_PER_LAUNCH = 6739712 + 967168
-NCU_DRAM_SOURCE = "profiles/r1r_walk_rollout_full.txt (ncu --set full, one launch, S=10000)"
+NCU_DRAM_BYTES_PER_LAUNCH = 6747648 + 881152
+NCU_DRAM_SOURCE = "profiles/r1s_walk_rollout_full.txt (ncu --set full, one launch, S=10000)"
 
 
 def workload_inputs(n_windows):
