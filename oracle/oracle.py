@@ -106,7 +106,7 @@ class Oracle:
         st = np.zeros((S, parents.shape[1])); cost = np.zeros(S); info = np.zeros((S, 5))
         t, tp = _d(target)
         lib().oc_window(self._h, _d(parents)[1], _d(actions)[1], tp, C.c_int(k0), C.c_int(k1), C.c_int(S // E),
-                        C.c_int(nsteps), _d(st)[1] if False else st.ctypes.data_as(C.POINTER(C.c_double)),
+                        C.c_int(nsteps), st.ctypes.data_as(C.POINTER(C.c_double)),
                         cost.ctypes.data_as(C.POINTER(C.c_double)), info.ctypes.data_as(C.POINTER(C.c_double)))
         return st[k0:k1], cost[k0:k1], info[k0:k1]
 

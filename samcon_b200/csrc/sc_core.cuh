@@ -950,7 +950,6 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
         float spec = 0.0f;
 #pragma unroll
         for (int s = 0; s < NRT; s++) {
-            constexpr int dummy = 0; (void)dummy;
             const int r = gs_row(s, NCT), c = r / 3, k = r - 3 * c, owner = s / RPL, m = s % RPL;
             // the owner's residual of this row: inside a run, the value formed from its own previous change
             const float rcur = m > 0 ? spec : res[m];
