@@ -145,3 +145,31 @@ def test_batched_multi_sequence_equals_single_runs(oracle):
     ref = SamCon(cfg, loaders[0], 1, 2, 12, 3, pool=OraclePool(oracle))
     out, info = ref.sample(save=False)
     np.testing.assert_allclose(out["x"]["path_0"]["cost"].reshape(-1), both[0]["cost"], rtol=1e-5)
+
+
+def test_result_pickles_have_the_reference_layout(oracle, motion, tmp_path):
+    """find_path_and_save writes the two joblib files the reference writes (trajectory.py:151-201): same directory
+    layout, keys, shapes and dtypes, so scripts/eval_samcon.py can consume them unchanged."""
+    import glob
+    import joblib
+    (name, _), = motion.items()
+    cfg = Config("walk", base_dir=str(tmp_path), cfg_dict=Config("walk").cfg_dict)
+    cfg.motion_seq = name
+    sc = SamCon(cfg, AmassMotionData(motion, name), 1, nIter=2, nSample=12, nSave=3, pool=OraclePool(oracle))
+    sc.sample(save=True)
+    (res_file,) = glob.glob(str(tmp_path / "results" / "samcon" / "walk" / "results" / "walk_*.pkl"))
+    (info_file,) = glob.glob(str(tmp_path / "results" / "samcon" / "walk" / "info" / "walk_*.pkl"))
+    out, info = joblib.load(res_file), joblib.load(info_file)
+    assert list(out) == [name] and sorted(out[name]) == ["path_0", "path_1", "path_2"]
+    p = out[name]["path_0"]
+    assert sorted(p) == ["action", "cost", "simulated_state", "t0_state", "target_state", "total_cost"]
+    assert p["target_state"].shape == (2, 132) and p["simulated_state"].shape == (2, 132)
+    assert p["action"].shape == (2, 68) and p["cost"].shape == (2, 1) and p["t0_state"].shape == (132,)
+    assert np.isclose(p["total_cost"], p["cost"].sum()) and all(v.dtype == np.float64 for k, v in p.items() if k != "total_cost")
+    costs = [out[name][f"path_{i}"]["total_cost"] for i in range(3)]
+    assert costs == sorted(costs)                                          # paths ordered by total cost (trajectory.py:147)
+    assert sorted(info) == ["balance_cost", "best_path_my_sys", "com_cost", "ee_cost", "elite_inds", "pose_cost",
+                            "root_cost", "total_cost"]
+    for k in ("pose_cost", "root_cost", "ee_cost", "balance_cost", "com_cost", "total_cost"):
+        assert info[k].shape == (2, 12)
+    assert info["elite_inds"].shape == (2, 3) and info["best_path_my_sys"].shape == (2,)
