@@ -129,3 +129,43 @@ def test_replay_determinism(pool, walk_cfg):
         state, cost, terms = env.step(p["action"][i])
         np.testing.assert_array_equal(state.astype(np.float32), p["simulated_state"][i].astype(np.float32))
         assert np.float32(cost) == np.float32(p["cost"][i])
+
+
+@pytest.mark.parametrize("variant", ["one_substep_few_iters", "low_friction_no_self", "scaled_character", "gaussian_noise"])
+def test_engine_and_model_parameters_reach_the_kernel(variant, walk_cfg):
+    """The kernel takes every engine / model number from the sc_model it was created with: other sub-step counts,
+    solver iterations, friction, erp, self collision off, a globalScaling-ed character (cfg `scale`), gaussian noise."""
+    import copy
+    from oracle.oracle import Oracle
+    from samcon_b200.model import Character, SimParams
+    from samcon_b200.pool import GpuSamplePool
+    from samcon_b200.sampling import get_batch_action
+    cfg = copy.copy(walk_cfg)
+    sim, z = None, 0.99
+    if variant == "one_substep_few_iters":
+        sim = SimParams(num_substeps=1, num_solver_iters=4, erp=0.1)
+    elif variant == "low_friction_no_self":
+        sim = SimParams(friction=0.3, self_collision=False, contact_threshold=0.01)
+    elif variant == "scaled_character":
+        cfg.scale, z = 1.2, 1.19
+    ch = Character.from_config(cfg, sim)
+    o = Oracle(ch)
+    pool = GpuSamplePool(ch, 0)
+    try:
+        rng = np.random.default_rng(31)
+        E, children = 4, 5
+        parents = np.array([stand(rng, 0.04, 0.2, z + 0.003 * i) for i in range(E)])
+        target = stand(rng, 0.03, 0.1, z)
+        if variant == "gaussian_noise":
+            actions = get_batch_action(target, E * children, 0.02 * np.ones(51), "gaussian", np.random.RandomState(2))
+        else:
+            actions = np.array([near_action(parents[k // children], rng, 0.1) for k in range(E * children)])
+        st, cost, info = pool.window(parents.astype(np.float32), actions.astype(np.float32), target.astype(np.float32), 60)
+        ost, ocost, oinfo = o.window(parents, actions, target, 60)
+        rms = joint_rms(st.cpu().numpy(), ost)
+        crel = np.abs(cost.cpu().numpy() - ocost) / np.abs(ocost)
+        print(f"{variant}: joint rms max {rms.max():.2e}, cost rel max {crel.max():.2e}")
+        assert rms.max() < 1e-3 and crel.max() < 1e-3
+        np.testing.assert_allclose(st.cpu().numpy()[:, :3], ost[:, :3], atol=2e-4)
+    finally:
+        pool.close()
