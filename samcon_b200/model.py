@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .urdf import BOX, CAPSULE, SPHERE, J_FIXED, J_FLOATING, J_SPHERICAL, Link
+from .urdf import BOX, CAPSULE, SPHERE, J_FIXED, J_SPHERICAL, Link
 
 STATE_DIM = 132          # humanoid_stable_pd.py:142-148
 MAX_LEVEL_WIDTH = 4      # articulated-inertia hand-over slots per tree level in the rollout kernel (ICW)

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from samcon_b200.sampling import actions_from_noise, draw_noise, get_batch_action
+from samcon_b200.sampling import draw_noise, get_batch_action
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "get_batch_action.npz"))
 CASES = ["walk_uniform", "cartwheel_uniform", "walk_gaussian"]

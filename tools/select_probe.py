@@ -1,4 +1,4 @@
-import sys, os, torch, numpy as np
+import sys, torch
 sys.path.insert(0,'/root/repo')
 from samcon_b200.config import Config
 from samcon_b200.model import Character
