@@ -285,7 +285,9 @@ def run_ours(args):
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    roofline = {"bound": "fp32-cuda-core (not hbm, not tensor: SURVEY.md §8d)", "achieved": kern_rate * FLOP_PER_SAMPLE_STEP / 1e12,
+    roofline = {"bound": "fp32", "bound_note": "FP32 CUDA-core pipe; neither hbm (0.004 % of DRAM peak) nor tensor (no dense "
+                                                  "contraction in a 57-DoF rigid-body step): SURVEY.md §8d, DESIGN.md §4",
+                "achieved": kern_rate * FLOP_PER_SAMPLE_STEP / 1e12,
                 "peak": fp32_peak, "unit": "TFLOP/s", "frac": kern_rate * FLOP_PER_SAMPLE_STEP / 1e12 / fp32_peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_DRAM_SOURCE,
                 "algorithmic_bytes_per_launch": S * STEPS_PER_WINDOW * BYTES_PER_SAMPLE_STEP,
