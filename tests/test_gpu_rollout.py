@@ -173,3 +173,31 @@ def test_select_edge_cases(pool):
         pool.select(c, 0)
     with pytest.raises((RuntimeError, ValueError)):
         pool.window(torch.zeros(3, 132, device="cuda"), torch.zeros(7, 68, device="cuda"), torch.zeros(132, device="cuda"), 1)
+
+
+def test_two_handles_and_a_side_stream(character, pool, oracle):
+    """Two pools (handles) on one device, one of them driven from a non-default stream: results equal the default
+    path bit for bit (entry points enqueue on the caller's stream and share nothing between handles)."""
+    import torch
+    from samcon_b200.pool import GpuSamplePool
+    rng = np.random.default_rng(12)
+    parents = torch.tensor(np.array([stand(rng, 0.05, 0.2, 0.99) for _ in range(6)]), dtype=torch.float32, device="cuda")
+    actions = torch.tensor(np.array([near_action(parents[k // 3].cpu().numpy(), rng, 0.1) for k in range(18)]),
+                           dtype=torch.float32, device="cuda")
+    target = torch.tensor(stand(rng), dtype=torch.float32, device="cuda")
+    ref = pool.window(parents, actions, target, 30)
+    other = GpuSamplePool(character, 0)
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            a = other.window(parents, actions, target, 30)
+            idx, ec = other.select(a[1], 6)
+        b = pool.window(parents, actions, target, 30)           # the first pool keeps working on the default stream
+        side.synchronize()
+        torch.cuda.synchronize()
+        for x, y, z in zip(ref, a, b):
+            assert torch.equal(x, y) and torch.equal(x, z)
+        assert idx[0].tolist() == torch.argsort(ref[1], stable=True)[:6].tolist()
+    finally:
+        other.close()
