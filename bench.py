@@ -47,7 +47,7 @@ def workload_inputs(n_windows):
     from samcon_b200.motion import AmassMotionData, make_synthetic_motion
     cfg = Config("walk")
     ch = Character.from_config(cfg)
-    motion = make_synthetic_motion("walk", T=91, fr=30, seed=0)
+    motion = make_synthetic_motion("gait", T=max(100, 3 * n_windows + 10), fr=30, seed=0)
     (name, _), = motion.items()
     loader = AmassMotionData(motion, name)
     targets = loader.all_window_states(n_windows, 1.0 / cfg.fps_act)

@@ -183,6 +183,7 @@ def _lowest_point(links, pose):
 def make_synthetic_motion(kind="walk", T=91, fr=30, seed=0, links=None, name=None):
     """-> {name: {'fr': fr, 'pose': (T,75)}}.
 
+    gait: the planted-foot walk of make_gait_motion (what solves and bench.py use).
     walk: upright SMPL-like gait, root travels along the facing direction (-Y world: the character's links hang
     along local -Y and toes point to local +Z, so the AMASS "upright" root rotation is +90 deg about X), hips
     +-0.45 rad at 1 Hz in antiphase, knees 0..0.8 rad, ankles compensating, shoulders swinging +-0.3 rad, small
@@ -190,6 +191,8 @@ def make_synthetic_motion(kind="walk", T=91, fr=30, seed=0, links=None, name=Non
     arms raised so that hands reach the ground, legs spread.
     Root height is set frame by frame so that the lowest collision point touches the ground.
     """
+    if kind == "gait":
+        return make_gait_motion(T=T, fr=fr, seed=seed, links=links, name=name)
     if links is None:
         from .urdf import load_links
         links = load_links(None)
@@ -253,3 +256,132 @@ def check_state(state):
     if s.shape[-1] != STATE_DIM:
         raise ValueError(f"expected {STATE_DIM}-float states")
     return s
+
+
+# ----------------------------------------------------------------------------------------------------------
+# planted-foot gait: a kinematically consistent synthetic walk (stance feet do not slide, pelvis sways over the
+# stance foot, the motion starts from standing).  The sinusoid walk above is kept for the parity tests that use
+# it as a source of poses; a SamCon *solve* needs a motion a physical character can follow.
+# ----------------------------------------------------------------------------------------------------------
+def _rot_x(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+
+
+def _rot_z(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+
+
+def _mat_to_quat(R):
+    from scipy.spatial.transform import Rotation as sRot
+    return sRot.from_matrix(R).as_quat()
+
+
+def _leg_ik(hip_org, knee_org, ankle_org, want, x0):
+    """(hip roll about z, hip flexion about x, knee flexion about x) such that the ankle joint sits at `want`
+    (pelvis frame).  Newton iterations with a finite-difference Jacobian, started from the previous frame."""
+    def ankle(x):
+        Rh = _rot_z(x[0]) @ _rot_x(x[1])
+        return hip_org + Rh @ (knee_org + _rot_x(x[2]) @ ankle_org)
+    x = np.array(x0, dtype=np.float64)
+    for _ in range(30):
+        e = ankle(x) - want
+        if np.linalg.norm(e) < 1e-10:
+            break
+        J = np.zeros((3, 3))
+        for k in range(3):
+            d = np.zeros(3); d[k] = 1e-6
+            J[:, k] = (ankle(x + d) - ankle(x - d)) / 2e-6
+        x = x - np.linalg.solve(J + 1e-9 * np.eye(3), e)
+        x[2] = max(x[2], 0.02)            # the knee only bends one way
+    return x
+
+
+def make_gait_motion(T=91, fr=30, seed=0, links=None, name=None, step_time=0.5, step_length=0.4, double_support=0.2,
+                     pelvis_height=0.93, half_width=0.09, sway=0.04, lift=0.06, ramp=0.3):
+    """-> {name: {'fr': fr, 'pose': (T,75)}}: a walk built from footholds.
+
+    The pelvis advances along the facing direction (-Y world) with speed step_length/step_time after a smooth start
+    from standing, sways towards the stance side, and each foot alternates between standing flat on its foothold
+    and a cycloidal swing to the next one; hip and knee angles come from inverse kinematics on the character's own
+    link offsets, the ankle keeps the sole level.  Arms swing against the legs.  `seed` varies step length, cadence
+    and sway by a few percent so that different seeds are different sequences.
+    """
+    if links is None:
+        from .urdf import load_links
+        links = load_links(None)
+    rng = np.random.default_rng(seed)
+    var = 1.0 + (0.05 * rng.standard_normal(3) if seed else np.zeros(3))
+    Ts, Ls, sway = step_time * var[0], step_length * var[1], sway * var[2]
+    v = Ls / Ts
+    name = name or f"synthetic_gait_{seed}"
+    idx = {l.name: i for i, l in enumerate(links)}
+    jorg = {n: links[idx[n]].jorg for n in idx}
+    sole = 0.09 + 0.001                                       # ankle joint above the ground when the sole is level
+
+    def progress(t):                                          # pelvis travel, velocity v (1 - exp(-t/ramp))
+        return v * (t - ramp * (1.0 - math.exp(-t / ramp)))
+
+    def gain(t):
+        return 1.0 - math.exp(-t / ramp)
+
+    # footholds: foot f (0 left, 1 right) swings during steps k = f, f+2, ...; it lands where the pelvis will be at
+    # the middle of the stance that follows
+    def stance_mid(k):                                        # foot that swings in step k stands from (k+1) Ts
+        return (k + 1) * Ts + 0.5 * (1.0 + double_support) * Ts
+
+    def foot(f, t):
+        """-> (forward position, height above the level stance) of foot f at time t"""
+        k = int(math.floor(t / Ts))
+        # last step (<= k) in which this foot swings
+        ks = k if k % 2 == f else k - 1
+        prev = progress(stance_mid(ks - 2)) if ks - 2 >= -1 and ks >= 2 else 0.0
+        if ks < 0:
+            return 0.0, 0.0
+        nxt = progress(stance_mid(ks))
+        if ks == k:                                           # swinging (after the double-support part of the step)
+            s = (t - k * Ts) / Ts
+            s = (s - double_support) / (1.0 - double_support)
+            if s <= 0:
+                return prev, 0.0
+            c = s - math.sin(2 * math.pi * s) / (2 * math.pi)
+            return prev + (nxt - prev) * c, lift * math.sin(math.pi * s) ** 2
+        return nxt, 0.0
+
+    up = _qx(0.5 * np.pi)
+    pose = np.zeros((T, 75))
+    x_prev = [np.array([0.0, -0.3, 0.6]), np.array([0.0, -0.3, 0.6])]
+    for fidx in range(T):
+        t = fidx / fr
+        px = -sway * gain(t) * math.sin(math.pi * (t - 0.5 * double_support * Ts) / Ts)   # towards the stance side
+        pz = progress(t)
+        q = {n: np.array([0.0, 0.0, 0.0, 1.0]) for n in JOINTS}
+        fz = []
+        for f, (hip, knee, ank) in enumerate((("lhip", "lknee", "lankle"), ("rhip", "rknee", "rankle"))):
+            z, h = foot(f, t)
+            fz.append(z - pz)
+            side = 1.0 if f == 0 else -1.0
+            want = np.array([side * half_width - px, sole + h - pelvis_height, z - pz])    # pelvis frame: x left, y up, z fwd
+            x = _leg_ik(jorg[hip], jorg[knee], jorg[ank], want, x_prev[f])
+            x_prev[f] = x
+            Rh = _rot_z(x[0]) @ _rot_x(x[1])
+            Rk = _rot_x(x[2])
+            q[hip] = _mat_to_quat(Rh)
+            q[knee] = _mat_to_quat(Rk)
+            q[ank] = _mat_to_quat((Rh @ Rk).T)              # sole level, toes forward
+        swing = 0.3 / 0.25
+        q["lshoulder"] = quat_mul(_qaxis([0, 0, 1], -1.2), _qx(swing * fz[1]))
+        q["rshoulder"] = quat_mul(_qaxis([0, 0, 1], 1.2), _qx(swing * fz[0]))
+        q["lelbow"] = _qaxis([0, 1, 0], -0.3)
+        q["relbow"] = _qaxis([0, 1, 0], 0.3)
+        pose[fidx, 0:3] = [px, -pz, pelvis_height]
+        pose[fidx, 3:7] = up
+        for k, n in enumerate(JOINTS):
+            pose[fidx, 7 + 4 * k:11 + 4 * k] = q[n]
+    for fidx in range(1, T):
+        for k in range(18):
+            a, b = pose[fidx - 1, 3 + 4 * k:7 + 4 * k], pose[fidx, 3 + 4 * k:7 + 4 * k]
+            if np.dot(a, b) < 0:
+                pose[fidx, 3 + 4 * k:7 + 4 * k] = -b
+    return {name: {"fr": fr, "pose": pose}}

@@ -33,10 +33,12 @@ if __name__ == "__main__":
     if args.synthetic or not os.path.exists(cfg.data_path):
         if not args.synthetic:
             print(f"{cfg.data_path} not found: solving the synthetic '{args.cfg}' motion (pass --synthetic to silence)")
-        motion = make_synthetic_motion("cartwheel" if "cartwheel" in args.cfg else "walk", T=91, fr=30, seed=0)
+        # generated long enough that the last window's target (t = nIter / fps_act) lies inside the cycle
+        motion = make_synthetic_motion("cartwheel" if "cartwheel" in args.cfg else "gait", T=3 * cfg.nIter + 10, fr=30, seed=0)
         (name, _), = motion.items()
         cfg.motion_seq = name
         data = AmassMotionData(motion, name)
+        cfg.auto_nIter = False
     else:
         data = AmassMotionData(cfg.data_path, cfg.motion_seq)
     if cfg.auto_nIter:
