@@ -8,8 +8,12 @@
  * Each entry point below names the reference call(s) it replaces.  All data pointers are DEVICE
  * pointers to contiguous float32 / int32 arrays owned by the caller (PyTorch tensors on the Python
  * side); every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
- * synchronising.  Return value: 0 on success, negative SC_E* otherwise; sc_last_error() gives text.
- * One handle per device and per host thread; handles are not thread-safe.
+ * synchronising (sc_contact_stats excepted); scratch buffers grow with cudaMallocAsync on that stream.
+ * Every call runs on the handle's device and restores the caller's current device before returning.
+ * Return value: 0 on success, negative SC_E* otherwise; sc_last_error() gives text.
+ * One handle per device and per host thread, used from ONE stream at a time (per-handle scratch is not
+ * per-stream: calls on a second stream must be ordered after the first by the caller); handles are
+ * not thread-safe.
  */
 #ifndef SAMCON_B200_H
 #define SAMCON_B200_H
@@ -26,6 +30,7 @@ extern "C" {
 #define SC_MAX_CAND 80    /* ground-contact candidate points */
 #define SC_MAX_CPOINTS 24 /* cost points = URDF links */
 #define SC_MAX_CONTACTS 8 /* per-sample cap, deepest first */
+#define SC_CACHE_DIM (2 * SC_MAX_CONTACTS) /* contact-cache row: candidate ids (as floats, -1 = empty), normal impulses */
 #define SC_MAX_PRIMS 24   /* self-collision primitives (sphere-swept segments) */
 #define SC_MAX_PAIRS 128  /* self-collision primitive pairs */
 
@@ -66,6 +71,8 @@ typedef struct sc_model {
     const float *prim;           /* [nprim,7] sphere-swept segment in the body frame: p0 xyz, p1 xyz, radius */
     const int32_t *pair;         /* [npair,2] primitive indices; links neither equal nor ancestor-related */
     float friction_self;         /* link lateral friction x link lateral friction */
+    float warmstart;             /* 0..1: factor on a persisting contact's cached normal impulse (0 = stateless contacts) */
+    float spinning_friction, spinning_friction_self; /* must be 0: the torsional row exists in the CPU oracle only */
 } sc_model;
 
 typedef struct sc_context *sc_handle;
@@ -76,37 +83,70 @@ int sc_create(sc_handle *out, const sc_model *model, int device);
 int sc_destroy(sc_handle h);
 const char *sc_last_error(sc_handle h);
 
-/* SamCon.get_batch_action -- samcon.py:101-142.  target [132]; limits [3*nj] (cfg joint_noises);
- * noise [S,3*nj] in [0,1) (the reference's np.random.random draw) or NULL to draw Philox-4x32-10 uniforms
- * from (seed, window); perm [S] row permutation (np.random.shuffle) or NULL; gaussian!=0 reads `noise`
- * as standard normals (or draws Box-Muller normals) scaled by sqrt(limits).  actions [S,4*nj] xyzw. */
-int sc_sample_gen(sc_handle h, const float *target, const float *limits, const float *noise, const int32_t *perm,
+/* SamCon.get_batch_action -- samcon.py:101-142, for nseq sequences at once (rows [q S, (q+1) S) belong to sequence q).
+ * targets [nseq,132]; limits [3*nj] (cfg joint_noises); noise [nseq*S,3*nj] in [0,1) (the reference's np.random.random
+ * draw) or NULL to draw Philox-4x32-10 uniforms keyed by (seed + q, window) and counted from the sequence's first row;
+ * perm [nseq*S] row permutation inside each sequence (np.random.shuffle) or NULL; gaussian!=0 reads `noise` as standard
+ * normals (or draws Box-Muller normals) scaled by sqrt(limits).  actions [nseq*S,4*nj] xyzw. */
+int sc_sample_gen(sc_handle h, const float *targets, int nseq, const float *limits, const float *noise, const int32_t *perm,
                   int gaussian, uint64_t seed, uint64_t window, int S, float *actions, void *stream);
 
-/* Worker "sim" for all samples of all sequences at once -- samcon.py:28-41 + env.step + cost
- * (humanoid_tracking_env.py:184-200, 78-176).  Sample k restores parents[parent_idx ? parent_idx[k] : k/children],
- * holds actions[k] for nsteps x {stable PD; stepSimulation}, and is scored against
- * targets[sample_seq ? sample_seq[k] : 0].  Outputs in sample order: out_state [S,132], out_cost [S],
- * out_info [S,5] = pose, root, ee, balance, com. */
-int sc_window(sc_handle h, const float *parents, int E, const int32_t *parent_idx, int children,
-              const float *actions, const float *targets, int nseq, const int32_t *sample_seq, int S, int nsteps,
-              float *out_state, float *out_cost, float *out_info, void *stream);
+/* AmassMotionData.getSpecTimeState for every (sequence, time) pair -- data_loaders/amass_motion_data.py:48-109 with the
+ * finite-difference velocities of utils/bullet_utils.py:9-45.  poses [sum of frames, 3+4*(nj+1)] = the sequences' (T,75)
+ * pose arrays one after the other (root position, root quaternion, joint quaternions, xyzw); frame_offsets [nseq+1] first
+ * row of each sequence; frame_dt [nseq] key-frame duration 1/fr (double); times [nt] query times in seconds (double).
+ * out [nseq, nt, 132] target states (cycling past the last frame with the cycle offset, like the reference). */
+int sc_motion_states(sc_handle h, const float *poses, const int32_t *frame_offsets, const double *frame_dt, int nseq,
+                     const double *times, int nt, float *out, void *stream);
 
-/* env.step without the cost: used by the replay facade (scripts/eval_samcon.py:67-81). state [S,132] in place. */
-int sc_step(sc_handle h, float *state, const float *actions, int S, int nsteps, void *stream);
+/* Worker "sim" for all samples of all sequences at once -- samcon.py:28-41 + env.step + cost
+ * (humanoid_tracking_env.py:184-200, 78-176).  Sample k restores parents[p] with p = parent_idx ? parent_idx[k] : k/children
+ * (restore_pb_state, humanoid_tracking_env.py:181-182: the .bullet snapshot carries the contact cache, so parent_cache[p]
+ * [E,SC_CACHE_DIM] is restored with it; NULL = empty caches, the first window), holds actions[k] for nsteps x {stable PD;
+ * stepSimulation}, and is scored against targets[sample_seq ? sample_seq[k] : 0].  Outputs in sample order: out_state
+ * [S,132], out_cost [S], out_info [S,5] = pose, root, ee, balance, com, out_cache [S,SC_CACHE_DIM] (save_pb_state,
+ * humanoid_tracking_env.py:178-179); any output may be NULL. */
+int sc_window(sc_handle h, const float *parents, const float *parent_cache, int E, const int32_t *parent_idx, int children,
+              const float *actions, const float *targets, int nseq, const int32_t *sample_seq, int S, int nsteps,
+              float *out_state, float *out_cost, float *out_info, float *out_cache, void *stream);
+
+/* env.step without the cost: used by the replay facade (scripts/eval_samcon.py:67-81). state [S,132] and cache
+ * [S,SC_CACHE_DIM] (or NULL: empty caches in, result dropped) are updated in place. */
+int sc_step(sc_handle h, float *state, float *cache, const float *actions, int S, int nsteps, void *stream);
+
+/* Diagnostic, SYNCHRONISES the device: out2[0] = sample-sub-steps in which more candidate points were inside the contact
+ * margin than max_contacts (the deepest were kept), out2[1] = sample-sub-steps simulated by sc_window / sc_step since the
+ * handle was created or last reset. */
+int sc_contact_stats(sc_handle h, int64_t *out2, int reset);
 
 /* compute_total_cost for explicit (sim, kin) pairs -- humanoid_tracking_env.py:78-90. out [S,6] total + 5 terms */
 int sc_cost(sc_handle h, const float *sim, const float *kin, int S, float *out, void *stream);
 
 /* Trajectory.select('greedy') -- /root/reference/samcon/core/trajectory.py:108-112, segmented: for each of nseg
  * segments [seg_offsets[i], seg_offsets[i+1]) writes the indices (global, into cost[]) of its E smallest costs
- * in ascending (cost, index) order to elite_idx[i*E ...].  NaN costs sort last.  scratch: see sc_select_scratch. */
+ * in ascending (cost, index) order to elite_idx[i*E ...] (a segment shorter than E: its entries, then -1 / +inf).  NaN costs
+ * sort last.  Scratch is owned by the handle and grows in stream order.
+ * total = seg_offsets[nseg] - seg_offsets[0], the number of costs the call looks at (the offsets live on the device; the
+ * host needs the figure to size the launch).  One cooperative launch: a segment is split over as many CTAs as its length
+ * needs, so a 10^6-sample window uses the whole GPU and 64 sequences are selected side by side. */
 int sc_select(sc_handle h, const float *cost, const int32_t *seg_offsets, int nseg, int E, int32_t *elite_idx,
-              float *elite_cost, void *stream);
+              float *elite_cost, int total, void *stream);
 
 /* restore_pb_state/save_pb_state replacement -- humanoid_tracking_env.py:178-182: rows of src [*,width] picked by
- * idx [n] are copied to dst [n,width] (elite states become next window's parents, all in HBM). */
+ * idx [n] are copied to dst [n,width] (elite states and contact caches become next window's parents, all in HBM);
+ * idx -1 (sc_select's padding) gives a zero row. */
 int sc_gather_rows(sc_handle h, const float *src, const int32_t *idx, int n, int width, float *dst, void *stream);
+
+/* The multi-GPU form of the same restore: row r of dst [n,width] = row src_row[r] of the [*,width] array at device address
+ * peer_base[src_peer[r]].  peer_base [npeer] holds addresses valid in THIS process -- the other ranks' result buffers
+ * mapped through CUDA VMM / symmetric memory -- so the elites' snapshots cross NVLink inside one gather kernel instead of
+ * a collective (the reference's master gathers every worker's pickled results, samcon.py:172-176). */
+int sc_gather_rows_peer(sc_handle h, const uint64_t *peer_base, const int32_t *src_peer, const int32_t *src_row, int n,
+                        int width, float *dst, void *stream);
+
+/* Measurement aid, SYNCHRONISES: FP32 FFMA throughput of `device` in TFLOP/s (a register-only FFMA loop on every SM, best of
+ * five), the measured counterpart of the nominal 148 x 128 x 2 x clock figure bench.py's roofline is quoted against. */
+int sc_measure_fp32_peak(int device, double *tflops);
 
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t sc_launch_count(sc_handle h);

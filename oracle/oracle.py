@@ -52,7 +52,9 @@ class Oracle:
         t = character.raw_tables()
         sp = character.sim
         simp = [sp.dt, sp.num_substeps, sp.num_solver_iters, *sp.gravity, sp.friction, sp.erp,
-                sp.contact_threshold, sp.max_contacts, sp.max_velocity, float(bool(sp.self_collision)), sp.friction_self]
+                sp.contact_threshold, sp.max_contacts, sp.max_velocity, float(bool(sp.self_collision)), sp.friction_self,
+                sp.warmstart, sp.spinning_friction, sp.spinning_friction_self]
+        self.cache_dim = 2 * sp.max_contacts
         keep = []
 
         def D(x):
@@ -83,12 +85,23 @@ class Oracle:
             pass
 
     # --- reference-shaped calls -------------------------------------------------------------
-    def step(self, state, action, nsteps=1):
-        """nsteps x {actuate(action); stepSimulation()} -> new 132-state."""
+    def step(self, state, action, nsteps=1, cache=None):
+        """nsteps x {actuate(action); stepSimulation()} -> new 132-state.  ``cache``: contact-cache row (2 * max_contacts
+        values, see empty_cache) updated in place, or None to start from an empty cache and drop the result."""
         s, sp = _d(np.array(state, dtype=np.float64, copy=True))
         a, ap = _d(action)
-        lib().oc_step(self._h, sp, ap, C.c_int(nsteps))
+        if cache is None:
+            lib().oc_step(self._h, sp, ap, C.c_int(nsteps))
+        else:
+            assert cache.dtype == np.float64 and cache.flags.c_contiguous and cache.shape == (self.cache_dim,)
+            lib().oc_step_cache(self._h, sp, ap, C.c_int(nsteps), cache.ctypes.data_as(C.POINTER(C.c_double)))
         return s
+
+    def empty_cache(self, n=None):
+        """Contact-cache rows with no contacts: ids -1, impulses 0."""
+        c = np.zeros((n or 1, self.cache_dim))
+        c[:, :self.cache_dim // 2] = -1.0
+        return c if n else c[0]
 
     def cost(self, sim, kin):
         """-> (total, [pose, root, ee, balance, com])"""
@@ -97,7 +110,9 @@ class Oracle:
         lib().oc_cost(self._h, sp, kp, out.ctypes.data_as(C.POINTER(C.c_double)))
         return out[0], out[1:]
 
-    def window(self, parents, actions, target, nsteps, k0=0, k1=None):
+    def window(self, parents, actions, target, nsteps, k0=0, k1=None, parent_cache=None, return_cache=False):
+        """Samples k0..k1 of one window.  ``parent_cache`` [E, cache_dim]: the parents' contact caches (None: empty);
+        with ``return_cache`` a fourth array [k1-k0, cache_dim] holds every sample's cache at the end of the window."""
         parents = np.ascontiguousarray(parents, dtype=np.float64)
         actions = np.ascontiguousarray(actions, dtype=np.float64)
         S, E = actions.shape[0], parents.shape[0]
@@ -105,9 +120,18 @@ class Oracle:
         k1 = S if k1 is None else k1
         st = np.zeros((S, parents.shape[1])); cost = np.zeros(S); info = np.zeros((S, 5))
         t, tp = _d(target)
-        lib().oc_window(self._h, _d(parents)[1], _d(actions)[1], tp, C.c_int(k0), C.c_int(k1), C.c_int(S // E),
-                        C.c_int(nsteps), st.ctypes.data_as(C.POINTER(C.c_double)),
-                        cost.ctypes.data_as(C.POINTER(C.c_double)), info.ctypes.data_as(C.POINTER(C.c_double)))
+        pc = None
+        if parent_cache is not None:
+            parent_cache = np.ascontiguousarray(parent_cache, dtype=np.float64)
+            assert parent_cache.shape == (E, self.cache_dim)
+            pc = parent_cache.ctypes.data_as(C.POINTER(C.c_double))
+        oc = np.zeros((S, self.cache_dim)) if return_cache else None
+        lib().oc_window_cache(self._h, _d(parents)[1], _d(actions)[1], tp, C.c_int(k0), C.c_int(k1), C.c_int(S // E),
+                              C.c_int(nsteps), st.ctypes.data_as(C.POINTER(C.c_double)),
+                              cost.ctypes.data_as(C.POINTER(C.c_double)), info.ctypes.data_as(C.POINTER(C.c_double)),
+                              pc, oc.ctypes.data_as(C.POINTER(C.c_double)) if return_cache else None)
+        if return_cache:
+            return st[k0:k1], cost[k0:k1], info[k0:k1], oc[k0:k1]
         return st[k0:k1], cost[k0:k1], info[k0:k1]
 
     @staticmethod

@@ -31,7 +31,8 @@
 #define MAXS 64
 #define MAXV 102
 #define MAXCAND 256
-#define MAXROW (3 * MAXCAND)
+#define MAXROW (4 * MAXCAND)
+#define MAXCC 64   /* contact-cache entries per sample (>= maxc) */
 #define MAXPAIR 512
 
 typedef struct {
@@ -46,10 +47,18 @@ typedef struct {
     /* self collision (URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS, humanoid_stable_pd.py:10-13) */
     int selfcol, npair, pair_a[MAXPAIR], pair_b[MAXPAIR];
     double mu_self, cap_p0[MAXS][3], cap_p1[MAXS][3], cap_r[MAXS];
+    /* contact persistence: warm-start factor applied to the cached normal impulse of a contact that was also present in
+     * the previous sub-step (0 = stateless contacts); spinning (torsional) friction coefficients, ground / link-link */
+    double warmstart, spin, spin_self;
 } oc_model;
 
 typedef struct {
     double p[3], Q[4], q[MAXL][4], vw[3], ww[3], w[MAXL][3];
+    /* contact cache: candidate id and normal impulse of every contact of the previous sub-step (what Bullet keeps in its
+     * persistent manifolds, btManifoldPoint::m_appliedImpulse; saved / restored with the world by saveBullet / restoreState,
+     * /root/reference/envs/humanoid_tracking_env.py:178-182) */
+    int ncache, cid[MAXCC];
+    double clam[MAXCC];
 } oc_state;
 
 typedef struct {
@@ -96,6 +105,12 @@ static void qmul(const double *a, const double *b, double *o) { /* o = a (x) b, 
 static void qnormalize(double *q) {
     double n = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     for (int i = 0; i < 4; i++) q[i] *= n;
+}
+/* state rows coming back from a previous call are unit to rounding and are left alone (a resumed window then repeats the
+ * uncut one exactly); anything else is normalised.  The threshold is the device's (float32 states). */
+static void qnormalize_input(double *q) {
+    double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (fabs(n2 - 1.0) > 1e-6) qnormalize(q);
 }
 /* exponential-map increment, Bullet's multibody quaternion update with its small-angle Taylor branch
  * [BULLET-UPSTREAM, unverified] */
@@ -200,7 +215,7 @@ oc_model *oc_create(int nl, const int *parent, const int *jtype, const double *j
                     const double *I_pd, int ns, const int *sh_link, const int *sh_kind, const double *sh_dims,
                     const double *sh_pos, const double *sh_rot, const double *kp, const double *kd,
                     const double *maxf,
-                    const double *simp /* dt,nsub,niter,gx,gy,gz,mu,erp,cthresh,maxc,maxvel,selfcol,mu_self */,
+                    const double *simp /* dt,nsub,niter,gx,gy,gz,mu,erp,cthresh,maxc,maxvel,selfcol,mu_self,warmstart,spin,spin_self */,
                     const double *jw, int nee, const int *ee, const double *cw, double height) {
     if (nl > MAXL || ns > MAXS) return NULL;
     oc_model *m = (oc_model *)calloc(1, sizeof(oc_model));
@@ -229,6 +244,7 @@ oc_model *oc_create(int nl, const int *parent, const int *jtype, const double *j
     m->nee = nee; for (int k = 0; k < nee; k++) m->ee[k] = ee[k];
     memcpy(m->cw, cw, 40); m->height = height;
     m->selfcol = (int)simp[11]; m->mu_self = simp[12];
+    m->warmstart = simp[13]; m->spin = simp[14]; m->spin_self = simp[15];
     self_collision_setup(m);
     return m;
 }
@@ -242,6 +258,21 @@ static void unpack(const oc_model *m, const double *s, oc_state *st) {
     for (int k = 0; k < nj; k++) memcpy(st->q[k], s + 7 + 4 * k, 32);
     memcpy(st->vw, s + 7 + 4 * nj, 24); memcpy(st->ww, s + 10 + 4 * nj, 24);
     for (int k = 0; k < nj; k++) memcpy(st->w[k], s + 13 + 4 * nj + 3 * k, 24);
+    st->ncache = 0;
+}
+/* contact-cache row (2 * maxc values): candidate ids (-1 = empty slot), then their normal impulses */
+static void cache_load(const oc_model *m, const double *row, oc_state *st) {
+    st->ncache = 0;
+    if (!row) return;
+    for (int i = 0; i < m->maxc && i < MAXCC; i++)
+        if (row[i] >= 0) { st->cid[st->ncache] = (int)row[i]; st->clam[st->ncache] = row[m->maxc + i]; st->ncache++; }
+}
+static void cache_store(const oc_model *m, const oc_state *st, double *row) {
+    if (!row) return;
+    for (int i = 0; i < m->maxc; i++) {
+        row[i] = i < st->ncache ? st->cid[i] : -1.0;
+        row[m->maxc + i] = i < st->ncache ? st->clam[i] : 0.0;
+    }
 }
 static void pack(const oc_model *m, const oc_state *st, double *s) {
     int nj = m->nj;
@@ -431,7 +462,7 @@ static void stable_pd(const oc_model *m, const oc_state *st, const oc_kin *k, co
  * plane_implicit.urdf at z = 0 (/root/reference/envs/humanoid_tracking_env.py:75-76).  Stateless
  * manifold: sphere -> lowest point, capsule -> lowest point of each cap, box -> corners; a point joins
  * the solve when its height is below the contact threshold; deepest `maxc` kept (ties: lower index). */
-typedef struct { int link, link2; double pos[3], pos2[3], n[3], dist, mu; } oc_contact;
+typedef struct { int link, link2, id; double pos[3], pos2[3], n[3], dist, mu, spin; } oc_contact;
 
 static double clamp01(double x) { return x < 0 ? 0 : (x > 1 ? 1 : x); }
 /* closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9); parallel segments: s = 0 */
@@ -473,7 +504,7 @@ static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
         double len = sqrt(dot3(d, d)), dist = len - m->cap_r[sa] - m->cap_r[sb];
         if (dist < m->cthresh && len > 1e-9 && n < MAXCAND) {
             oc_contact *cc = &cand[n++];
-            cc->link = la; cc->link2 = lb; cc->dist = dist; cc->mu = m->mu_self;
+            cc->link = la; cc->link2 = lb; cc->dist = dist; cc->mu = m->mu_self; cc->spin = m->spin_self; cc->id = pi;
             for (int a = 0; a < 3; a++) {
                 cc->n[a] = d[a] / len;
                 cc->pos[a] = c1[a] - m->cap_r[sa] * cc->n[a];
@@ -481,7 +512,8 @@ static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
             }
         }
     }
-    /* ground */
+    /* ground; candidate id = npair + running index of the (shape, point) */
+    int gid = m->npair;
     for (int s = 0; s < m->ns; s++) {
         int l = m->sh_link[s];
         double c[3], t[3];
@@ -502,8 +534,10 @@ static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
             mv3(Rs, loc, pw);
             for (int a = 0; a < 3; a++) pw[a] += c[a];
             pw[2] -= r;
+            const int this_id = gid++;
             if (pw[2] < m->cthresh && n < MAXCAND) {
                 oc_contact *cc = &cand[n++];
+                cc->id = this_id; cc->spin = m->spin;
                 cc->link = l; cc->link2 = -1; memcpy(cc->pos, pw, 24); memcpy(cc->pos2, pw, 24);
                 cc->n[0] = 0; cc->n[1] = 0; cc->n[2] = 1; cc->dist = pw[2]; cc->mu = m->mu;
             }
@@ -543,6 +577,22 @@ static void contact_row(const oc_model *m, const oc_kin *k, const oc_contact *c,
     point_row_acc(m, k, c->link, c->pos, d, 1.0, J);
     if (c->link2 >= 0) point_row_acc(m, k, c->link2, c->pos2, d, -1.0, J);
 }
+/* spinning-friction row: n . (omega(link) - omega(link2)) = J . v_gen (angular only) */
+static void spin_row(const oc_model *m, const oc_kin *k, const oc_contact *c, double *J) {
+    memset(J, 0, sizeof(double) * m->nv);
+    for (int side = 0; side < 2; side++) {
+        int link = side ? c->link2 : c->link;
+        double sgn = side ? -1.0 : 1.0;
+        if (link < 0) continue;
+        for (int a = link; a >= 0; a = m->parent[a]) {
+            if (m->dof[a] < 0) continue;
+            for (int e = 0; e < 3; e++) {
+                double ax[3] = {k->R[a][e], k->R[a][3 + e], k->R[a][6 + e]};
+                J[m->dof[a] + e] += sgn * dot3(ax, c->n);
+            }
+        }
+    }
+}
 /* Bullet's btPlaneSpace1: two unit tangents p, q for a unit normal n */
 static void plane_space(const double *n, double *p, double *q) {
     if (fabs(n[2]) > 0.7071067811865475244008443621048490) {
@@ -565,7 +615,8 @@ static double g_last_normal_impulse = 0, g_last_tangent_impulse[2] = {0, 0};   /
 static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const double *tau, double h) {
     static __thread double M[MAXV * MAXV], MinvJt[MAXROW][MAXV], J[MAXROW][MAXV];
     static __thread oc_contact con[MAXCAND];
-    double C[MAXV], rhs[MAXV], qdd[MAXV], v[MAXV], dv[MAXV], b[MAXROW], diag[MAXROW], lam[MAXROW];
+    double C[MAXV], rhs[MAXV], qdd[MAXV], v[MAXV], dv[MAXV];
+    static __thread double b[MAXROW], diag[MAXROW], lam[MAXROW];
     int nv = m->nv;
     int nc = collide(m, k, con);
     g_last_contacts = nc;
@@ -582,6 +633,9 @@ static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const doub
     for (int i = 0; i < nv; i++) v[i] += h * qdd[i];
 
     if (nc > 0) {
+        /* rows 3c+d: normal (d = 0) and the two lateral friction directions of contact c; row 3 nc + c: spinning
+         * (torsional) friction about the normal, angular only, for contacts with a spinning coefficient */
+        int has_spin[MAXCAND], nspin = 0;
         for (int c = 0; c < nc; c++) for (int d = 0; d < 3; d++) {
             int r = 3 * c + d;
             double dirs[3][3]; /* n, btPlaneSpace1(n): (0,0,1) -> (0,-1,0), (1,0,0) */
@@ -597,16 +651,39 @@ static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const doub
             b[r] = err / dg;
             lam[r] = 0;
         }
+        for (int c = 0; c < nc; c++) {
+            int r = 3 * nc + c;
+            has_spin[c] = con[c].spin > 0;
+            lam[r] = 0;
+            if (!has_spin[c]) continue;
+            nspin++;
+            spin_row(m, k, &con[c], J[r]);
+            chol_solve(M, nv, J[r], MinvJt[r]);
+            double dg = 0, rel = 0;
+            for (int i = 0; i < nv; i++) { dg += J[r][i] * MinvJt[r][i]; rel += J[r][i] * v[i]; }
+            diag[r] = dg; b[r] = -rel / dg;
+        }
         memset(dv, 0, sizeof(double) * nv);
+        /* warm start: a contact that was in the previous sub-step's list starts from `warmstart` x its normal impulse;
+         * friction rows start from zero (Bullet's multibody contact setup: isFriction ? 0 : m_appliedImpulse * factor) */
+        if (m->warmstart > 0)
+            for (int c = 0; c < nc; c++)
+                for (int o = 0; o < st->ncache; o++) if (st->cid[o] == con[c].id) {
+                    lam[3 * c] = m->warmstart * st->clam[o];
+                    for (int i = 0; i < nv; i++) dv[i] += MinvJt[3 * c][i] * lam[3 * c];
+                    break;
+                }
         for (int it = 0; it < m->niter; it++) {
-            for (int pass = 0; pass < 2; pass++)
-                for (int c = 0; c < nc; c++) for (int d = (pass ? 1 : 0); d < (pass ? 3 : 1); d++) {
-                    int r = 3 * c + d;
+            for (int pass = 0; pass < 3; pass++)     /* all normals, then the spinning rows, then the friction pairs */
+                for (int c = 0; c < nc; c++) for (int d = (pass == 2 ? 1 : 0); d < (pass == 2 ? 3 : 1); d++) {
+                    int r = pass == 1 ? 3 * nc + c : 3 * c + d;
+                    if (pass == 1 && !has_spin[c]) continue;
                     double jv = 0;
                     for (int i = 0; i < nv; i++) jv += J[r][i] * dv[i];
                     double nl = lam[r] + b[r] - jv / diag[r];
                     double lo = 0, hi = 1e30;
-                    if (d) { hi = con[c].mu * lam[3 * c]; lo = -hi; }
+                    if (pass == 2) { hi = con[c].mu * lam[3 * c]; lo = -hi; }
+                    if (pass == 1) { hi = con[c].spin * lam[3 * c]; lo = -hi; }
                     if (nl < lo) nl = lo;
                     if (nl > hi) nl = hi;
                     double dl = nl - lam[r];
@@ -614,6 +691,7 @@ static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const doub
                     for (int i = 0; i < nv; i++) dv[i] += MinvJt[r][i] * dl;
                 }
         }
+        (void)nspin;
         for (int i = 0; i < nv; i++) v[i] += dv[i];
         g_last_normal_impulse = 0; g_last_tangent_impulse[0] = g_last_tangent_impulse[1] = 0;
         for (int c = 0; c < nc; c++) if (con[c].link2 < 0) {
@@ -621,6 +699,9 @@ static void substep(const oc_model *m, oc_state *st, const oc_kin *k, const doub
             g_last_tangent_impulse[0] += lam[3 * c + 2]; g_last_tangent_impulse[1] -= lam[3 * c + 1];   /* world x, y */
         }
     } else { g_last_normal_impulse = 0; g_last_tangent_impulse[0] = g_last_tangent_impulse[1] = 0; }
+    /* the cache now describes this sub-step */
+    st->ncache = nc < MAXCC ? nc : MAXCC;
+    for (int c = 0; c < st->ncache; c++) { st->cid[c] = con[c].id; st->clam[c] = lam[3 * c]; }
     /* back to the stored representation, clamp, integrate (semi-implicit Euler) */
     mv3(k->R[0], v, st->ww);
     mv3(k->R[0], v + 3, st->vw);
@@ -654,14 +735,18 @@ static void step_state(const oc_model *m, oc_state *st, const double *action, in
     }
 }
 
-void oc_step(const oc_model *m, double *state, const double *action, int nsteps) {
+/* cache: contact-cache row (2 * maxc values) read before and rewritten after the steps, or NULL (empty cache in) */
+void oc_step_cache(const oc_model *m, double *state, const double *action, int nsteps, double *cache) {
     oc_state st;
     unpack(m, state, &st);
-    qnormalize(st.Q);
-    for (int j = 0; j < m->nj; j++) qnormalize(st.q[j]);
+    cache_load(m, cache, &st);
+    qnormalize_input(st.Q);
+    for (int j = 0; j < m->nj; j++) qnormalize_input(st.q[j]);
     step_state(m, &st, action, nsteps);
     pack(m, &st, state);
+    cache_store(m, &st, cache);
 }
+void oc_step(const oc_model *m, double *state, const double *action, int nsteps) { oc_step_cache(m, state, action, nsteps, NULL); }
 int oc_last_contacts(void) { return g_last_contacts; }
 void oc_last_ground_impulse(double *out3) { out3[0] = g_last_tangent_impulse[0]; out3[1] = g_last_tangent_impulse[1]; out3[2] = g_last_normal_impulse; }
 
@@ -730,19 +815,27 @@ void oc_cost(const oc_model *m, const double *sim, const double *kin, double *ou
 
 /* ------------------------------------------------------------------ one SamCon window for a slice of samples
  * /root/reference/samcon/core/samcon.py:28-41: sample k restores elite k / (S/E), steps, is scored. */
-void oc_window(const oc_model *m, const double *parents /* [E,132] */, const double *actions /* [S,68] */,
-               const double *target, int k0, int k1, int children, int nsteps, double *out_state, double *out_cost,
-               double *out_info) {
-    int sd = 13 + 7 * m->nj, ad = 4 * m->nj;
+void oc_window_cache(const oc_model *m, const double *parents /* [E,132] */, const double *actions /* [S,68] */,
+                     const double *target, int k0, int k1, int children, int nsteps, double *out_state, double *out_cost,
+                     double *out_info, const double *parent_cache /* [E, 2 maxc] or NULL */, double *out_cache /* [S, 2 maxc] or NULL */) {
+    int sd = 13 + 7 * m->nj, ad = 4 * m->nj, cw = 2 * m->maxc;
     for (int k = k0; k < k1; k++) {
-        double s[256], c[6];
+        double s[256], c[6], cache[2 * MAXCC];
         memcpy(s, parents + (size_t)(k / children) * sd, sizeof(double) * sd);
-        oc_step(m, s, actions + (size_t)k * ad, nsteps);
+        if (parent_cache) memcpy(cache, parent_cache + (size_t)(k / children) * cw, sizeof(double) * cw);
+        else for (int i = 0; i < cw; i++) cache[i] = i < m->maxc ? -1.0 : 0.0;
+        oc_step_cache(m, s, actions + (size_t)k * ad, nsteps, cache);
+        if (out_cache) memcpy(out_cache + (size_t)k * cw, cache, sizeof(double) * cw);
         oc_cost(m, s, target, c);
         memcpy(out_state + (size_t)k * sd, s, sizeof(double) * sd);
         out_cost[k] = c[0];
         memcpy(out_info + (size_t)k * 5, c + 1, 40);
     }
+}
+
+void oc_window(const oc_model *m, const double *parents, const double *actions, const double *target, int k0, int k1,
+               int children, int nsteps, double *out_state, double *out_cost, double *out_info) {
+    oc_window_cache(m, parents, actions, target, k0, k1, children, nsteps, out_state, out_cost, out_info, NULL, NULL);
 }
 
 /* elite selection: /root/reference/samcon/core/trajectory.py:108-112, ties broken by index */

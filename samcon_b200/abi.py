@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_CSRC, "libsamcon_b200.so")
 SC_STATE_DIM = 132
 SC_MAX_BODIES = 18
 SC_MAX_CONTACTS = 8
+SC_CACHE_DIM = 2 * SC_MAX_CONTACTS
 
 i32p = C.POINTER(C.c_int32)
 f32p = C.POINTER(C.c_float)
@@ -34,7 +35,8 @@ class ScModel(C.Structure):
         ("gravity", C.c_float * 3), ("friction", C.c_float), ("erp", C.c_float), ("contact_threshold", C.c_float),
         ("max_velocity", C.c_float),
         ("nprim", C.c_int32), ("npair", C.c_int32), ("prim_body", i32p), ("prim", f32p), ("pair", i32p),
-        ("friction_self", C.c_float),
+        ("friction_self", C.c_float), ("warmstart", C.c_float), ("spinning_friction", C.c_float),
+        ("spinning_friction_self", C.c_float),
     ]
 
 
@@ -73,12 +75,14 @@ def make_model(character):
     m.prim_body, m.prim = I(t["prim_body"]), F(t["prim"])
     m.pair = I(t["pair"] if len(t["pair"]) else np.zeros((1, 2)))
     m.friction_self = sp.friction_self
+    m.warmstart, m.spinning_friction, m.spinning_friction_self = sp.warmstart, sp.spinning_friction, sp.spinning_friction_self
     return m, keep
 
 
 # every entry point include/samcon_b200.h declares
 SYMBOLS = ["sc_create", "sc_destroy", "sc_last_error", "sc_sample_gen", "sc_window", "sc_step", "sc_cost",
-           "sc_select", "sc_gather_rows", "sc_launch_count", "sc_rollout_config"]
+           "sc_select", "sc_gather_rows", "sc_launch_count", "sc_rollout_config", "sc_contact_stats", "sc_motion_states", "sc_gather_rows_peer",
+           "sc_measure_fp32_peak"]
 
 _lib = None
 
@@ -100,12 +104,16 @@ def load():
     lib.sc_destroy.argtypes = [vp]
     lib.sc_last_error.argtypes = [vp]
     lib.sc_last_error.restype = C.c_char_p
-    lib.sc_sample_gen.argtypes = [vp, vp, vp, vp, vp, i, u64, u64, i, vp, vp]
-    lib.sc_window.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, i, i, vp, vp, vp, vp]
-    lib.sc_step.argtypes = [vp, vp, vp, i, i, vp]
+    lib.sc_sample_gen.argtypes = [vp, vp, i, vp, vp, vp, i, u64, u64, i, vp, vp]
+    lib.sc_motion_states.argtypes = [vp, vp, vp, vp, i, vp, i, vp, vp]
+    lib.sc_window.argtypes = [vp, vp, vp, i, vp, i, vp, vp, i, vp, i, i, vp, vp, vp, vp, vp]
+    lib.sc_step.argtypes = [vp, vp, vp, vp, i, i, vp]
+    lib.sc_contact_stats.argtypes = [vp, C.POINTER(C.c_int64), i]
     lib.sc_cost.argtypes = [vp, vp, vp, i, vp, vp]
-    lib.sc_select.argtypes = [vp, vp, vp, i, i, vp, vp, vp]
+    lib.sc_select.argtypes = [vp, vp, vp, i, i, vp, vp, i, vp]
     lib.sc_gather_rows.argtypes = [vp, vp, vp, i, i, vp, vp]
+    lib.sc_gather_rows_peer.argtypes = [vp, vp, vp, vp, i, i, vp, vp]
+    lib.sc_measure_fp32_peak.argtypes = [i, C.POINTER(C.c_double)]
     lib.sc_launch_count.argtypes = [vp]
     lib.sc_launch_count.restype = C.c_int64
     lib.sc_rollout_config.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]

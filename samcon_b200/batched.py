@@ -23,10 +23,10 @@ from .sampling import get_batch_action
 
 class BatchedSamCon:
 
-    def __init__(self, cfg, data_loaders, pool, nIter=None, nSample=None, nSave=None, device_noise=True, search=None):
+    def __init__(self, cfg, data_loaders, pool, nIter=None, nSample=None, nSave=None, device_noise=True, seed_offset=0):
         """``data_loaders``: one AmassMotionData-like object per sequence (``getSpecTimeState(t)``);
-        ``pool``: a GpuSamplePool;  ``search``: optional ``distributed.ShardedSearch`` factory is not needed here --
-        sequences, not samples, are what one would shard across GPUs for this mode."""
+        ``pool``: a GpuSamplePool.  Sequences, not samples, are what is sharded across GPUs in this mode
+        (``distributed.solve_sequences_sharded``): every rank runs this class on its share, no collective."""
         self._cfg = cfg
         self._loaders = list(data_loaders)
         self._pool = pool
@@ -41,6 +41,7 @@ class BatchedSamCon:
         self.children = self.S // self.E
         self.steps = cfg.fps_sim // cfg.fps_act
         self._device_noise = device_noise
+        self._seed_offset = int(seed_offset)      # first sequence's stream: a rank that solves sequences [q0, q0+Q) passes q0
         self._rngs = [np.random.RandomState(cfg.seed) for _ in range(self.Q)]  # np.random.seed(cfg.seed) per run
         dev = pool.device
         Q, S, E = self.Q, self.S, self.E
@@ -49,19 +50,23 @@ class BatchedSamCon:
         self._parent_idx = ((k // S) * E + (k % S) // self.children).contiguous()
         self._seg = (torch.arange(Q + 1, device=dev, dtype=torch.int32) * S).contiguous()
         dt = 1.0 / cfg.fps_act
-        tg = np.stack([np.stack([ld.getSpecTimeState(t * dt) for t in range(self.nIter + 1)]) for ld in self._loaders])
-        self.targets_host = tg                                               # [Q, nIter+1, 132]
-        self._targets = torch.tensor(tg, dtype=torch.float32, device=dev)
+        times = np.arange(self.nIter + 1, dtype=np.float64) * dt
+        if hasattr(pool, "motion_states") and all(hasattr(ld, "_motion") for ld in self._loaders):
+            # slerp + finite differences for all Q x (nIter + 1) targets in one launch (sc_motion_states)
+            self._targets = pool.motion_states(self._loaders, times)
+            self.targets_host = self._targets.cpu().numpy().astype(np.float64)       # [Q, nIter+1, 132]
+        else:
+            tg = np.stack([np.stack([ld.getSpecTimeState(t) for t in times]) for ld in self._loaders])
+            self.targets_host = tg
+            self._targets = torch.tensor(tg, dtype=torch.float32, device=dev)
         self._limits = torch.tensor(np.asarray(cfg.values), dtype=torch.float32, device=dev)
 
     def _actions(self, t):
         Q, S = self.Q, self.S
-        if self._device_noise:
-            act = torch.empty((Q * S, self._pool.act_dim), dtype=torch.float32, device=self._pool.device)
-            for q in range(Q):
-                self._pool.sample_gen(self._targets[q, t], self._limits, S, gaussian=self._cfg.noise_type == "gaussian",
-                                      seed=self._cfg.seed + q, window=t, out=act[q * S:(q + 1) * S])
-            return act
+        if self._device_noise:      # one launch for all sequences; sequence q draws from the stream (seed + q, t)
+            return self._pool.sample_gen(self._targets[:, t, :].contiguous(), self._limits, S,
+                                         gaussian=self._cfg.noise_type == "gaussian", seed=self._cfg.seed + self._seed_offset,
+                                         window=t)
         host = np.concatenate([get_batch_action(self.targets_host[q, t], S, self._cfg.values, self._cfg.noise_type,
                                                 self._rngs[q]) for q in range(Q)])
         return torch.tensor(host, dtype=torch.float32, device=self._pool.device)
@@ -72,30 +77,39 @@ class BatchedSamCon:
         (nIter,132), ``t0_state`` (132,), ``total_cost``; plus ``elite_cost`` (nIter, nSave)."""
         pool, Q, S, E = self._pool, self.Q, self.S, self.E
         parents = self._targets[:, 0, :].repeat_interleave(E, dim=0).contiguous()          # every elite slot = t0 state
+        pcache = None                                                                      # contact caches of the parents
         hist = []
         for t in range(1, self.nIter + 1):
             act = self._actions(t)
-            st, cost, info = pool.window(parents, act, self._targets[:, t, :].contiguous(), self.steps,
-                                         parent_idx=self._parent_idx, sample_seq=self._sample_seq)
+            st, cost, info, cache = pool.window(parents, act, self._targets[:, t, :].contiguous(), self.steps,
+                                                parent_idx=self._parent_idx, sample_seq=self._sample_seq,
+                                                parent_cache=pcache, out_cache=True)
             idx, ecost = pool.select(cost, E, seg_offsets=self._seg)                       # [Q,E] global sample ids
             flat = idx.reshape(-1)
             parents = pool.gather_rows(st, flat)
+            pcache = pool.gather_rows(cache, flat)
             eact = pool.gather_rows(act, flat)
             eparent = (flat.to(torch.int64) % S) // self.children                         # elite slot of window t-1
             hist.append((parents, eact, ecost, eparent.reshape(Q, E)))
-        # ---- best path per sequence: back-trace from the cheapest elite of the last window (trajectory.py:118-154)
+        # ---- best path per sequence (trajectory.py:118-154): back-trace every elite of the last window through the
+        # stored parent slots, sum the cost along each path, take the cheapest (stable ties, like find_paths' argsort)
         H = [(p.reshape(Q, E, STATE_DIM).cpu().numpy().astype(np.float64), a.reshape(Q, E, -1).cpu().numpy().astype(np.float64),
               c.cpu().numpy().astype(np.float64), e.cpu().numpy()) for p, a, c, e in hist]
         out = []
         for q in range(Q):
-            e = 0
-            sim, acts, costs = [], [], []
-            for t in range(self.nIter - 1, -1, -1):
-                P, A, Cc, Ep = H[t]
-                sim.append(P[q, e]); acts.append(A[q, e]); costs.append(Cc[q, e])
-                e = int(Ep[q, e])
-            sim.reverse(); acts.reverse(); costs.reverse()
+            slots = np.zeros((self.nIter, E), dtype=np.int64)          # slots[t, j]: elite slot of path j in window t+1
+            slots[-1] = np.arange(E)
+            for t in range(self.nIter - 1, 0, -1):
+                slots[t - 1] = H[t][3][q, slots[t]]
+            total = np.zeros(E)
+            for t in range(self.nIter):
+                total += H[t][2][q, slots[t]]
+            j = int(np.argsort(total, kind="stable")[0])
+            sim = [H[t][0][q, slots[t, j]] for t in range(self.nIter)]
+            acts = [H[t][1][q, slots[t, j]] for t in range(self.nIter)]
+            costs = [H[t][2][q, slots[t, j]] for t in range(self.nIter)]
             out.append({"simulated_state": np.array(sim), "action": np.array(acts), "cost": np.array(costs),
                         "target_state": self.targets_host[q, 1:], "t0_state": self.targets_host[q, 0],
-                        "total_cost": float(np.sum(costs)), "elite_cost": np.stack([h[2][q] for h in H])})
+                        "total_cost": float(np.sum(costs)), "elite_cost": np.stack([h[2][q] for h in H]),
+                        "path_total_costs": total})
         return out

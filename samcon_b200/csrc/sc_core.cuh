@@ -96,7 +96,7 @@ struct Tables {
     int cand_body[SC_MAX_CAND], cp_body[SC_MAX_CPOINTS], ee[4];
     float jorg[NB * 3], idyn[NB * 10], ipd[NB * 10], kp[NB], kd[NB], maxf[NB], cand[SC_MAX_CAND * 4];
     float cp_off[SC_MAX_CPOINTS * 3], cp_mass[SC_MAX_CPOINTS], jw[NB], cw[5];
-    float height, dt, h, g[3], mu, mu_self, erp, cthresh, maxvel, inv_total_mass;
+    float height, dt, h, g[3], mu, mu_self, erp, cthresh, maxvel, inv_total_mass, warmstart;
     SelfTables self;
 };
 
@@ -117,7 +117,9 @@ constexpr int O_TW = O_RJ + 3 * NB;               // body twist, world axes: ome
 constexpr int O_WJ = O_TW + 6 * NB - 3;           // joint angular velocity in world axes, R_b * w (3, b>=1)
 constexpr int O_TAU = O_WJ + 3 * NB - 3;          // child-frame joint torque held over the sub-steps; during the
                                                   // stable-PD solve: Kp*err - Kd*w (3, b>=1)
-constexpr int O_UA = O_TAU + 3 * NB - 6;          // articulated inertia (world axes), angular block (sym 6, b>=1)
+constexpr int O_UA = O_TAU + 3 * NB - 6;          // articulated inertia (world axes), angular block (sym 6, b>=1): written and read
+                                                  // by the stable-PD pass only (the dynamics pass has K A = 1); its words carry the
+                                                  // contact list during the sub-steps, see O_CB below
 constexpr int O_UB = O_UA + 6 * NB - 9;           // articulated inertia, linear-from-angular block (9, b>=1)
 constexpr int O_DI = O_UB + 9 * NB - 6;           // (S^T IA S + armature)^-1 (sym 6, b>=1)
 constexpr int O_I0L = O_DI + 6 * NB;              // Cholesky factor of the base articulated inertia (21)
@@ -128,15 +130,24 @@ constexpr int O_IC = O_I0L + 21;                  // articulated-inertia contrib
 constexpr int O_PC = O_IC + 21 * 2 * ICW;         // bias-force contribution to the parent (6); later: accelerations
 constexpr int O_UU = O_PC + 6 * NB - 3;           // u = tau - S^T pA (3, b>=1); contact apply: -S^T pa
 constexpr int O_SCR_END = O_UU + 3 * NB;
-constexpr int O_CB = O_SCR_END;                   // contact bodies (int): body a | (body b + 1) << 8, b = -1: the ground
-constexpr int O_CR = O_CB + MAXC;                 // contact point relative to the body origin, world axes (3)
+// contact cache: survives from one sub-step to the next, across the stable-PD pass and (through parent_cache /
+// out_cache) from one window to the next -- what Bullet keeps in its persistent manifolds and saveBullet stores
+constexpr int O_PCU = O_SCR_END;                  // candidate id of contact j (int): the current list once collide's cache stage ran
+constexpr int O_PLAM = O_PCU + MAXC;              // its normal impulse: warm-start value before the sweep, result after it
+constexpr int O_PNC = O_PLAM + MAXC;              // number of cached contacts (int)
+constexpr int O_OVF = O_PNC + 1;                  // sub-steps of this sample with more candidate hits than max_contacts (int)
+constexpr int O_END_DEV = O_OVF + 1;
+// contact list of the current sub-step, in the words of O_UA (dead between two stable-PD passes)
+constexpr int O_CB = O_UA + 6;                    // contact bodies (int): body a | (body b + 1) << 8, b = -1: the ground
+constexpr int O_CU = O_CB + MAXC;                 // candidate id (int): primitive pair u < npair, else npair + ground point
+constexpr int O_CR = O_CU + MAXC;                 // contact point relative to the body origin, world axes (3)
 constexpr int O_CD = O_CR + 3 * MAXC;             // signed distance
 constexpr int O_NC = O_CD + MAXC;                 // number of contacts (int)
 constexpr int O_TM = O_NC + 1;                    // mask of bodies on a root path of some contact (int), | TM_TWO_BODY
 constexpr int TM_TWO_BODY = 1 << 30;              // some contact of the sample is link-vs-link
-constexpr int O_RHS = O_TM + 1;
-constexpr int O_LAM = O_RHS + NR;
-constexpr int O_END_DEV = O_LAM + NR;
+constexpr int O_RHS = O_TM + 1;                   // right-hand sides; the sweep overwrites them with the impulses:
+constexpr int O_LAM = O_RHS;                      // a lane reads the rows it owns before the sweep and writes the same rows after it
+static_assert(O_RHS + NR <= O_UB + 9, "the contact list must fit in the words of O_UA");
 constexpr int O_AM = O_IC;                        // contact-space matrix, packed lower triangle (contact solve)
 constexpr int O_ZC = O_IC;                        // collide: signed distance per candidate (pairs, then ground points) ...
 constexpr int O_CNT = O_ZC + SC_MAX_CAND + NPAIR; // ... hits per lane (ground, pairs) ...
@@ -151,7 +162,7 @@ constexpr int O_FEAT = O_RHS;                     // end of window: com(3) comve
 static_assert(NR * (NR + 1) / 2 <= O_SCR_END - O_IC, "AM must fit in the scratch block");
 static_assert(O_PCEN + 3 * NPRIM <= O_SCR_END, "collide scratch must fit in the scratch block");
 static_assert(O_CN + 3 * MAXC <= O_WJ + 3 * NB, "second-body contact data must fit in WJ");
-static_assert(18 <= 2 * NR, "FEAT must fit in RHS + LAM");
+static_assert(18 <= NR, "FEAT must fit in RHS");
 #if defined(__CUDACC__)
 constexpr int O_END = O_END_DEV;
 #else
@@ -430,7 +441,8 @@ SC_DEV void aba_backward_body(float *S, const Tables &T, int b, const bool PD) {
     const V3 u = mul(R, ld3(S, O_TAU + 3 * b)) - pn;      // child-frame torque (PD: Kp err - Kd w) in world axes
     const V3 wj = ld3(S, O_WJ + 3 * b);
     const V3 cw = cross(w, wj), cv = cross(v, wj);
-    stS(S, O_UA + 6 * b, A); stM(S, O_UB + 9 * b, B); stS(S, O_DI + 6 * b, K); st3(S, O_UU + 3 * b, u);
+    if (PD) stS(S, O_UA + 6 * b, A);      // the dynamics pass never reads it back (K A = 1): its words hold the contact list
+    stM(S, O_UB + 9 * b, B); stS(S, O_DI + 6 * b, K); st3(S, O_UU + 3 * b, u);
     // Articulated inertia seen by the parent, IA - IA S (S^T IA S + arm)^-1 S^T IA with S = [1; 0] and K = (A + arm 1)^-1.
     // K commutes with A and A K = 1 - arm K, so with P = arm K:
     //   Aa = A - A K A = arm (1 - P),   Ba = B - B K A = arm B K,   Ca = C - B K B^T,   A K u = u - P u
@@ -661,6 +673,7 @@ SC_DEV void write_contact(float *S, const Tables &T, const SelfTables &ST, int j
         st3(S, O_CN + 3 * j, n);
     }
     F(O_CD + j) = z;
+    F(O_CU + j) = i2f(u);
 }
 
 template <class TT>
@@ -766,7 +779,10 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
                     }
                 }
         }
-        if (slot == 0) F(O_NC) = i2f(total);
+        if (slot == 0) {
+            F(O_NC) = i2f(total);
+            if (total > T.maxc) F(O_OVF) = i2f(f2i(F(O_OVF)) + 1);
+        }
     }
     SC_SYNC();
     if (tile_max_int(sm, O_NC) <= T.maxc) return;
@@ -825,6 +841,37 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
                 }
         }
         if (slot == 0 && total > T.maxc) F(O_NC) = i2f(T.maxc);
+    }
+    SC_SYNC();
+}
+
+// Contact cache (every sub-step, after collide): contact j of the new list starts the sweep from warmstart x the normal
+// impulse the same candidate ended the previous sub-step with (0 if it is new), and the cache is rewritten to describe the
+// new list.  O_RHS is free at this point and carries the values over the barrier.
+template <class TT>
+SC_PHASE void contact_cache(float *sm, const TT &T, int L0, int L1) {
+    static_assert(MAXC <= LPS * 2, "two contacts per lane at most");
+    SC_STAGE {
+        SC_LANE;
+        const int nc = f2i(F(O_NC)), pnc = f2i(F(O_PNC));
+        for (int j = slot; j < MAXC; j += LPS) {
+            float l0 = 0.0f;
+            if (j < nc) {
+                const int u = f2i(F(O_CU + j));
+                for (int o = 0; o < pnc; o++) if (f2i(F(O_PCU + o)) == u) l0 = T.warmstart * F(O_PLAM + o);
+            }
+            F(O_RHS + j) = l0;
+        }
+    }
+    SC_SYNC();
+    SC_STAGE {
+        SC_LANE;
+        const int nc = f2i(F(O_NC));
+        for (int j = slot; j < MAXC; j += LPS) {
+            F(O_PLAM + j) = F(O_RHS + j);
+            F(O_PCU + j) = j < nc ? F(O_CU + j) : i2f(-1);
+        }
+        if (slot == 0) F(O_PNC) = i2f(nc);
     }
     SC_SYNC();
 }
@@ -941,10 +988,22 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
         }
         res[m] = live ? F(O_RHS + row) : 0.0f;
         dgi[m] = live ? 1.0f / F(O_AM + row * (row + 1) / 2 + row) : 0.0f;
-        lam[m] = 0.0f;
+    }
+    // warm start: the normal rows begin at the cached impulses (contact_cache), friction rows at zero
+#pragma unroll
+    for (int c = 0; c < NCT; c++) {
+        lamn[c] = 3 * c < nr ? F(O_PLAM + c) : 0.0f;
+        muc[c] = (f2i(F(O_CB + c)) >> 8) ? T.mu_self : T.mu;
+#pragma unroll
+        for (int m = 0; m < RPL; m++) res[m] -= a[m][3 * c] * lamn[c];
     }
 #pragma unroll
-    for (int c = 0; c < NCT; c++) { lamn[c] = 0.0f; muc[c] = (f2i(F(O_CB + c)) >> 8) ? T.mu_self : T.mu; }
+    for (int m = 0; m < RPL; m++) {
+        const int row = gs_row(RPL * slot + m, NCT);
+        lam[m] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCT; c++) if (row == 3 * c) lam[m] = lamn[c];
+    }
     const int src0 = lane & (TILE - 1);
     for (int it = 0; it < T.niter; it++) {
         float spec = 0.0f;
@@ -968,7 +1027,10 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
 #pragma unroll
     for (int m = 0; m < RPL; m++) {
         const int row = gs_row(RPL * slot + m, NCT);
-        if (row < nr) F(O_LAM + row) = lam[m];
+        if (row < nr) {
+            F(O_LAM + row) = lam[m];          // same words as the right-hand sides this lane read above
+            if (row % 3 == 0) F(O_PLAM + row / 3) = lam[m];
+        }
     }
     __syncwarp();
 }
@@ -990,7 +1052,6 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
             F(O_RHS + 3 * j) = -dot(fr.d[0], vp) - (dist > 0 ? dist / T.h : dist * T.erp / T.h);
             F(O_RHS + 3 * j + 1) = -dot(fr.d[1], vp);
             F(O_RHS + 3 * j + 2) = -dot(fr.d[2], vp);
-            F(O_LAM + 3 * j) = 0; F(O_LAM + 3 * j + 1) = 0; F(O_LAM + 3 * j + 2) = 0;
         }
         if (slot == LPS - 1) {
             int mask = 0;
@@ -1038,8 +1099,19 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
         const int nc = f2i(F(O_NC));
         for (int r = slot; r < 3 * nc; r += LPS) {
             F(O_DGI + r) = 1.0f / F(O_AM + r * (r + 1) / 2 + r);
-            F(O_RES + r) = F(O_RHS + r);
+            float res = F(O_RHS + r);
+            for (int c = 0; c < nc; c++) {
+                const int cc = 3 * c, hi = r > cc ? r : cc, lo = r > cc ? cc : r;
+                res -= F(O_AM + hi * (hi + 1) / 2 + lo) * F(O_PLAM + c);
+            }
+            F(O_RES + r) = res;
         }
+    }
+    SC_SYNC();
+    SC_STAGE {      // O_LAM shares its words with O_RHS: start values go in once the residuals are formed
+        SC_LANE;
+        const int nc = f2i(F(O_NC));
+        for (int r = slot; r < 3 * nc; r += LPS) F(O_LAM + r) = (r % 3 == 0) ? F(O_PLAM + r / 3) : 0.0f;
     }
     SC_SYNC();
     const int per_iter = 3 * ncmax, total = T.niter * per_iter;
@@ -1080,6 +1152,12 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
         }
         SC_SYNC();
     }
+    SC_STAGE {
+        SC_LANE;
+        const int nc = f2i(F(O_NC));
+        for (int c = slot; c < nc; c += LPS) F(O_PLAM + c) = F(O_LAM + 3 * c);
+    }
+    SC_SYNC();
 #endif
     }
     if (part != 2) return;
@@ -1206,21 +1284,40 @@ SC_DEV int state_word(const Tables &T, int i) {
 }
 
 template <class TT>
-SC_DEV void load_state(float *sm, const TT &T, int L0, int L1, const float *rows, const int *parent_idx, int children, int tile0, int S_total) {
+SC_DEV void load_state(float *sm, const TT &T, int L0, int L1, const float *rows, const float *cache_rows, const int *parent_idx,
+                       int children, int tile0, int S_total) {
     SC_STAGE {
         SC_LANE;
         int k = tile0 + (lane & (TILE - 1));
         if (k >= S_total) k = S_total - 1;   // padding lanes replay the last sample and never write
-        const float *src = rows + (size_t)(parent_idx ? parent_idx[k] : k / children) * SC_STATE_DIM;
+        const size_t pr = (size_t)(parent_idx ? parent_idx[k] : k / children);
+        const float *src = rows + pr * SC_STATE_DIM;
         for (int i = slot; i < SC_STATE_DIM; i += LPS) F(state_word(T, i)) = src[i];
+        // contact cache row: MAXC candidate ids (as floats, -1 = empty, filled from the front), MAXC normal impulses
+        const float *cr = cache_rows ? cache_rows + pr * SC_CACHE_DIM : nullptr;
+        for (int j = slot; j < MAXC; j += LPS) {
+            F(O_PCU + j) = i2f(cr ? (int)cr[j] : -1);
+            F(O_PLAM + j) = cr ? cr[MAXC + j] : 0.0f;
+        }
+        if (slot == 0) {
+            int n = 0;
+            if (cr) for (int j = 0; j < MAXC; j++) n += cr[j] >= 0.0f ? 1 : 0;
+            F(O_PNC) = i2f(n);
+            F(O_OVF) = i2f(0);
+        }
     }
     SC_SYNC();
     SC_STAGE {
         SC_LANE;
         for (int b = slot; b < T.nb; b += LPS) {
             const int o = O_Q + 4 * b;
-            const float n = rsq(F(o) * F(o) + F(o + 1) * F(o + 1) + F(o + 2) * F(o + 2) + F(o + 3) * F(o + 3));
-            F(o) *= n; F(o + 1) *= n; F(o + 2) *= n; F(o + 3) *= n;
+            // a quaternion this kernel wrote comes back unit to rounding and is left alone, so that resuming from
+            // (state, cache) reproduces the uncut run bit for bit; anything else (host data) is normalised
+            const float n2 = F(o) * F(o) + F(o + 1) * F(o + 1) + F(o + 2) * F(o + 2) + F(o + 3) * F(o + 3);
+            if (fabsf(n2 - 1.0f) > 1e-6f) {
+                const float n = rsq(n2);
+                F(o) *= n; F(o + 1) *= n; F(o + 2) *= n; F(o + 3) *= n;
+            }
         }
     }
     SC_SYNC();
@@ -1300,6 +1397,7 @@ SC_DEV void cost_terms(const float *S, const Tables &T, const float *kin, const 
 // ============================================================================================================
 struct RolloutArgs {
     const float *parents;      // [E,132]
+    const float *parent_cache; // [E,SC_CACHE_DIM] contact caches of the parents, or null (empty caches)
     const int *parent_idx;     // [S] or null
     int children;
     const float *actions;      // [S,4*nj]
@@ -1310,6 +1408,8 @@ struct RolloutArgs {
     float *out_state, *out_cost, *out_info;   // any may be null
     float *out_feat;           // [S,18] or null (feature-only mode)
     float *out_cost6;          // [S,6] total + 5 terms, or null (sc_cost)
+    float *out_cache;          // [S,SC_CACHE_DIM] or null
+    unsigned long long *stats; // [2] or null: sample-sub-steps with more candidate hits than max_contacts, sample-sub-steps
     long long *prof;           // developer builds (-DSC_PROFILE): per-phase cycle counters, else null
 };
 
@@ -1324,7 +1424,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
         }
         return;
     }
-    load_state(sm, T, L0, L1, a.parents, a.parent_idx, a.children, tile0, a.S);
+    load_state(sm, T, L0, L1, a.parents, a.parent_cache, a.parent_idx, a.children, tile0, a.S);
     SC_T(0);
     for (int step = 0; step < a.nsteps; step++) {
         SC_BAR(1);
@@ -1352,6 +1452,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             SC_T(30);
             // positions are those of the start of the sub-step; the ABA's scratch is free for the collision pass now
             collide(sm, T, T.self, L0, L1 SC_PROF_PASS);
+            contact_cache(sm, T, L0, L1);
             SC_T(4);
             const int ncmax = tile_max_int(sm, O_NC);
 #if defined(SC_PROFILE) && defined(__CUDACC__)
@@ -1382,6 +1483,16 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
                 for (int i = slot; i < SC_STATE_DIM; i += LPS) dst[i] = F(state_word(T, i));
             }
             if (a.out_feat) for (int i = slot; i < 18; i += LPS) a.out_feat[(size_t)k * 18 + i] = F(O_FEAT + i);
+            if (a.out_cache) {
+                float *dst = a.out_cache + (size_t)k * SC_CACHE_DIM;
+                for (int j = slot; j < MAXC; j += LPS) { dst[j] = (float)f2i(F(O_PCU + j)); dst[MAXC + j] = F(O_PLAM + j); }
+            }
+#if defined(__CUDACC__)
+            if (a.stats && slot == 0 && a.nsteps > 0) {
+                atomicAdd(a.stats, (unsigned long long)f2i(F(O_OVF)));
+                atomicAdd(a.stats + 1, (unsigned long long)a.nsteps * T.nsub);
+            }
+#endif
             if (slot == 0 && (a.out_cost || a.out_cost6)) {
                 const int q = a.sample_seq ? a.sample_seq[k] : 0;
                 float c[6];

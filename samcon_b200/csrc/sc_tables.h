@@ -69,6 +69,10 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
     for (int k = 0; k < 3; k++) T->g[k] = m->gravity[k];
     T->mu = m->friction; T->mu_self = m->friction_self; T->erp = m->erp; T->cthresh = m->contact_threshold; T->maxvel = m->max_velocity;
     T->inv_total_mass = (float)(1.0 / tm);
+    if (!(m->warmstart >= 0.0f && m->warmstart <= 1.0f)) SC_FAIL("warmstart=%g outside 0..1", (double)m->warmstart);
+    T->warmstart = m->warmstart;
+    if (m->spinning_friction != 0.0f || m->spinning_friction_self != 0.0f)
+        SC_FAIL("spinning friction is not implemented on the device (3 rows per contact); use 0");
     // self collision: primitives with bounding spheres, pairs with their broad-phase radius
     if (m->npair < 0 || m->npair > NPAIR) SC_FAIL("npair=%d outside 0..%d", m->npair, NPAIR);
     if (m->npair > 0) {

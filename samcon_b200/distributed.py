@@ -9,37 +9,92 @@ window is elite selection:
   1. every rank takes its local top-min(E, S_loc) (cost, index) with the segmented radix top-k kernel,
   2. NCCL all_gather of those (cost f32, index i32) lists  (8 B x E per rank),
   3. every rank runs the identical final top-E over the N*E candidates (ties: lower global sample index),
-  4. winners' states are exchanged: each rank writes the rows it owns into a zero [E,132] buffer and one
-     NCCL all_reduce(sum) delivers every winning state to every rank (x + 0 is exact), of which rank r keeps
-     its parent block.
+  4. rank r fetches the snapshots (132-float state + contact cache) of ITS parent block -- E_loc rows, wherever they
+     were simulated -- straight out of the owners' result buffers over NVLink: the buffers live in symmetric memory
+     (torch.distributed._symmetric_memory, CUDA VMM handles exchanged once at start-up) and one gather kernel
+     (sc_gather_rows_peer) reads peer HBM through NVSwitch.  No collective, no padding, no host synchronisation:
+     E_loc x 592 B per rank per window.  The all_gather of step 2 is what orders the traffic: a rank's contribution
+     is sent after its rollout finished (same stream), so once the all_gather has completed every peer's buffer is
+     complete; result buffers alternate between two copies from window to window so that a fast rank's next rollout
+     never overwrites rows a slow rank is still reading (the next all_gather cannot complete before the slow rank
+     has enqueued its contribution, which follows its reads in stream order).
+     Where symmetric memory is unavailable (gloo in the CPU tests, or a torch without it) the rows travel by ONE
+     all_to_all_single of fixed-size blocks instead (each rank sends every peer the rows of that peer's block it owns,
+     zero elsewhere; the receiver adds the N blocks -- every row has exactly one owner, x + 0 is exact).
 
 All steps are enqueued on the current stream; there is no host synchronisation inside a window.
 ``torch.distributed`` is plumbing only (NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
+from .abi import SC_CACHE_DIM as CACHE_DIM
 from .model import STATE_DIM
+
+ROW = STATE_DIM + CACHE_DIM      # a sample's snapshot: state + contact cache
 
 
 class ShardedSearch:
-    def __init__(self, pool, S_local: int, E_global: int, rank: int, world: int, group=None):
+    def __init__(self, pool, S_local: int, E_global: int, rank: int, world: int, group=None, exchange: str = "auto"):
         if E_global % world or S_local % (E_global // world):
             raise ValueError("nSave must split evenly over ranks and nSample over elites")
         self.pool, self.S_loc, self.E, self.rank, self.world, self.group = pool, S_local, E_global, rank, world, group
         self.E_loc = E_global // world
         self.Ec = min(E_global, S_local)          # candidates a rank can contribute
+        self.exchange = "local" if world == 1 else None
+        self._win = 0
+        self._snap = None
+        dev = getattr(pool, "device", torch.device("cpu"))
+        if world > 1 and exchange in ("auto", "p2p") and dev.type == "cuda" and hasattr(pool, "gather_rows_peer"):
+            try:
+                self._setup_symmetric(dev)
+                self.exchange = "nvlink-p2p"
+            except Exception as e:                # noqa: BLE001 -- any failure means: use the collective
+                if exchange == "p2p":
+                    raise
+                self._symm_error = repr(e)
+        if self.exchange is None:
+            self.exchange = "all_to_all"
+        if self._snap is None:
+            n = self.S_loc * ROW
+            self._snap = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
 
-    def select_and_exchange(self, st, cost):
-        """(st [S_loc,132], cost [S_loc]) of this rank -> (all elite states [E,132], elite global sample ids [E],
-        elite costs [E]); identical on every rank."""
+    # ------------------------------------------------------------------ symmetric result buffers
+    def _setup_symmetric(self, dev):
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        n = self.S_loc * ROW
+        self._snap, self._peer_state, self._peer_cache, self._hdl = [], [], [], []
+        for _ in range(2):
+            t = symm.empty(n, dtype=torch.float32, device=dev)
+            hdl = symm.rendezvous(t, group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world:
+                raise RuntimeError("symmetric memory rendezvous returned the wrong number of peers")
+            self._snap.append(t)
+            self._hdl.append(hdl)
+            self._peer_state.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
+            self._peer_cache.append(torch.tensor([p + 4 * self.S_loc * STATE_DIM for p in ptrs], dtype=torch.int64, device=dev))
+
+    def result_buffers(self):
+        """(state [S_loc,132], cache [S_loc,CACHE_DIM]) views of this window's snapshot buffer."""
+        b = self._snap[self._win & 1]
+        ns = self.S_loc * STATE_DIM
+        return b[:ns].view(self.S_loc, STATE_DIM), b[ns:].view(self.S_loc, CACHE_DIM)
+
+    # ------------------------------------------------------------------ the exchange
+    def select_global(self, cost):
+        """Local top-Ec, all_gather of (cost, index), identical final top-E on every rank.
+        -> (owner rank [E] int32, row in the owner's buffers [E] int32, cost [E], global sample id [E] int64)."""
         dev = cost.device
         lidx, lcost = self.pool.select(cost, self.Ec)
         lidx, lcost = lidx.reshape(-1), lcost.reshape(-1)
         if self.world == 1:
-            return self.pool.gather_rows(st, lidx[:self.E]), lidx[:self.E].to(torch.int64), lcost[:self.E]
+            return torch.zeros(self.E, dtype=torch.int32, device=dev), lidx[:self.E].contiguous(), lcost[:self.E], lidx[:self.E].to(torch.int64)
         # flat [world * Ec] outputs: the layout both NCCL and gloo accept for a 1-D input
         all_cost = torch.empty((self.world * self.Ec,), dtype=torch.float32, device=dev)
         all_idx = torch.empty((self.world * self.Ec,), dtype=torch.int32, device=dev)
@@ -47,20 +102,63 @@ class ShardedSearch:
         dist.all_gather_into_tensor(all_idx, lidx.contiguous(), group=self.group)
         pos, gcost = self.pool.select(all_cost, self.E)
         pos = pos.reshape(-1).to(torch.int64)
-        win_rank = pos // self.Ec
-        win_local = all_idx.reshape(-1)[pos].to(torch.int64)
-        mine = win_rank == self.rank
-        buf = torch.zeros((self.E, STATE_DIM), dtype=torch.float32, device=dev)
-        # rows this rank owns; the masked local index is clamped so the gather stays in range
-        rows = self.pool.gather_rows(st, torch.where(mine, win_local, torch.zeros_like(win_local)).to(torch.int32))
-        buf = torch.where(mine[:, None], rows, buf)
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-        return buf, win_rank * self.S_loc + win_local, gcost.reshape(-1)
+        win_rank = (pos // self.Ec).to(torch.int32)
+        win_local = all_idx[pos].contiguous()
+        return win_rank, win_local, gcost.reshape(-1), win_rank.to(torch.int64) * self.S_loc + win_local.to(torch.int64)
 
-    def window(self, parent_block, actions, target, nsteps):
-        """One sharded window.  parent_block [E_loc,132] are this rank's parents.  Returns
-        (next parent block [E_loc,132], elite ids [E], elite costs [E], (st, cost, info) of the local samples)."""
-        st, cost, info = self.pool.window(parent_block, actions, target, nsteps)
-        elites, ids, ecost = self.select_and_exchange(st, cost)
-        blk = elites[self.rank * self.E_loc:(self.rank + 1) * self.E_loc].contiguous()
-        return blk, ids, ecost, (st, cost, info)
+    def fetch_block(self, win_rank, win_local, st, cache):
+        """Snapshots of this rank's parent block: (states [E_loc,132], caches [E_loc,CACHE_DIM])."""
+        lo, hi = self.rank * self.E_loc, (self.rank + 1) * self.E_loc
+        if self.world == 1:
+            return self.pool.gather_rows(st, win_local[lo:hi]), self.pool.gather_rows(cache, win_local[lo:hi])
+        if self.exchange == "nvlink-p2p":
+            p = self._win & 1
+            r, l = win_rank[lo:hi].contiguous(), win_local[lo:hi].contiguous()
+            return (self.pool.gather_rows_peer(self._peer_state[p], r, l, STATE_DIM),
+                    self.pool.gather_rows_peer(self._peer_cache[p], r, l, CACHE_DIM))
+        # collective fall-back: block d of the send buffer = the rows of rank d's parent block that live here
+        dev = st.device
+        mine = win_rank == self.rank
+        safe = torch.where(mine, win_local, torch.zeros_like(win_local)).to(torch.int32)
+        rows = torch.cat([self.pool.gather_rows(st, safe), self.pool.gather_rows(cache, safe)], dim=1)      # [E, ROW]
+        send = torch.where(mine[:, None], rows, torch.zeros((), dtype=torch.float32, device=dev)).contiguous()
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)                  # recv[s*E_loc + j] = rank s's copy of my row j
+        blk = recv.view(self.world, self.E_loc, ROW).sum(dim=0)
+        return blk[:, :STATE_DIM].contiguous(), blk[:, STATE_DIM:].contiguous()
+
+    def select_and_exchange(self, st, cost, cache=None):
+        """(st [S_loc,132], cost [S_loc], cache [S_loc,CACHE_DIM]) of this rank -> (parent block states [E_loc,132], parent
+        block caches, elite global sample ids [E], elite costs [E]); ids and costs identical on every rank."""
+        if cache is None:
+            cache = torch.zeros((st.shape[0], CACHE_DIM), dtype=torch.float32, device=st.device)
+            cache[:, :CACHE_DIM // 2] = -1.0
+        win_rank, win_local, gcost, gid = self.select_global(cost)
+        bst, bcache = self.fetch_block(win_rank, win_local, st, cache)
+        self._win += 1
+        return bst, bcache, gid, gcost
+
+    def window(self, parent_block, actions, target, nsteps, parent_cache=None):
+        """One sharded window.  parent_block [E_loc,132] (+ parent_cache [E_loc,CACHE_DIM]) are this rank's parents.
+        Returns (next parent block, next parent caches, elite ids [E], elite costs [E], (st, cost, info) of the local
+        samples -- st is a view of this window's snapshot buffer, valid until the window after next)."""
+        st, cache = self.result_buffers()
+        dev = st.device
+        cost = torch.empty((self.S_loc,), dtype=torch.float32, device=dev)
+        info = torch.empty((self.S_loc, 5), dtype=torch.float32, device=dev)
+        self.pool.window(parent_block, actions, target, nsteps, out=(st, cost, info), parent_cache=parent_cache, out_cache=cache)
+        bst, bcache, ids, ecost = self.select_and_exchange(st, cost, cache)
+        return bst, bcache, ids, ecost, (st, cost, info)
+
+
+def solve_sequences_sharded(cfg, data_loaders, pool, rank: int, world: int, **kw):
+    """BASELINE config 5 on N GPUs: the Q sequences are dealt to the ranks in contiguous blocks and every rank solves its
+    share with BatchedSamCon -- sequences are independent searches, so there is no data-path collective at all.
+    Sequence q draws from the Philox stream (cfg.seed + q) whichever rank solves it.  -> (first sequence index, results)."""
+    from .batched import BatchedSamCon
+    Q = len(data_loaders)
+    per = (Q + world - 1) // world
+    q0, q1 = min(Q, rank * per), min(Q, (rank + 1) * per)
+    if q1 <= q0:
+        return q0, []
+    return q0, BatchedSamCon(cfg, data_loaders[q0:q1], pool, seed_offset=q0, **kw).sample()

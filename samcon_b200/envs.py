@@ -16,8 +16,9 @@ from .model import STATE_DIM, Character
 class _Agent:
     """State holder with HumanoidStablePD's set_state/get_state and pQvw accessors."""
 
-    def __init__(self, nj):
+    def __init__(self, nj, on_set=None):
         self._nj = nj
+        self._on_set = on_set
         self._state = np.zeros(STATE_DIM)
         self._state[6] = 1.0
         self._state[10:7 + 4 * nj:4] = 1.0
@@ -27,6 +28,8 @@ class _Agent:
         state = np.array(state, dtype=np.float64)
         assert state.shape == (STATE_DIM,)
         self._state = state
+        if self._on_set:
+            self._on_set()
 
     def get_state(self):
         return self._state.copy()
@@ -63,8 +66,14 @@ class HumanoidTrackingEnv:
             pool = GpuSamplePool(Character.from_config(cfg), 0)
         self._pool = pool
         nj = (STATE_DIM - 13) // 7
-        self._sim_agent = _Agent(nj)
+        # the world's contact cache lives between step() calls like Bullet's manifolds do; teleporting the simulated
+        # character (set_state) drops it
+        self._cache = None
+        self._sim_agent = _Agent(nj, self._drop_cache)
         self._kin_agent = _Agent(nj)
+
+    def _drop_cache(self):
+        self._cache = None
 
     def compute_total_cost(self):
         c = self._pool.cost(self._sim_agent.get_state().astype(np.float32)[None],
@@ -73,10 +82,12 @@ class HumanoidTrackingEnv:
 
     def step(self, action):
         action = np.asarray(action, dtype=np.float32).reshape(1, -1)
-        st, cost, info = self._pool.window(self._sim_agent.get_state().astype(np.float32)[None], action,
-                                           self._kin_agent.get_state().astype(np.float32), self._num_substep, children=1)
+        st, cost, info, cache = self._pool.window(self._sim_agent.get_state().astype(np.float32)[None], action,
+                                                  self._kin_agent.get_state().astype(np.float32), self._num_substep,
+                                                  children=1, parent_cache=self._cache, out_cache=True)
         simulated_state = st.cpu().numpy()[0].astype(np.float64)
         self._sim_agent.set_state(simulated_state)
+        self._cache = cache
         return simulated_state, float(cost.cpu().numpy()[0]), [float(x) for x in info.cpu().numpy()[0]]
 
     def close(self):

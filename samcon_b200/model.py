@@ -42,6 +42,19 @@ class SimParams:
     max_velocity: float = 100.0       # btMultiBody max coordinate velocity clamp
     self_collision: bool = True       # URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS (humanoid_stable_pd.py:10-13)
     friction_self: float = 0.8 * 0.8  # link lateral 0.8 x link lateral 0.8 (product rule)
+    # Contact persistence (saveBullet / restoreState carry the contact cache, humanoid_tracking_env.py:178-182, 69-71):
+    # a contact that was also present in the previous sub-step starts the Gauss-Seidel sweep from warmstart x its last
+    # normal impulse; 0 = stateless contacts (round 1).  SURVEY.md §9.2 lists "warm-starting on (factor 0.85)"
+    # [BULLET-UPSTREAM, unverified: bullet3's btMultiBodyConstraintSolver::setupMultiBodyContactConstraint has carried its
+    # warm start behind a disabled branch in several releases -- set 0.0 to restate that].
+    warmstart: float = 0.85
+    # spinning (torsional) friction about the contact normal: humanoid_stable_pd.py:66-76 sets spinningFriction 0.3 on
+    # every link; combined coefficient per contact [BULLET-UPSTREAM, unverified] = sum over the two objects of
+    # spinningFriction x lateralFriction = 0.3 x 0.8 against the plane (which has none), 2 x 0.3 x 0.8 link-vs-link.
+    # Only the CPU oracle implements the row (it is 0 by default: the device contact solve holds 3 rows per contact in
+    # registers and sc_create rejects a non-zero value).
+    spinning_friction: float = 0.0
+    spinning_friction_self: float = 0.0
 
 
 def _skew(v):
@@ -174,8 +187,14 @@ class Character:
     def from_config(cls, cfg, sim: SimParams | None = None, **kw):
         from .urdf import load_links
         links = load_links(cfg.model_file, cfg.scale, search_dirs=(getattr(cfg, "base_dir", ""),))
-        if sim is None:     # cfg key self_collision (walk.yml:113) -> loadURDF flags, humanoid_stable_pd.py:10-13
-            sim = SimParams(self_collision=bool(getattr(cfg, "self_collision", True)))
+        # setTimeStep(1 / cfg.fps_sim) (humanoid_tracking_env.py:25, 46); cfg key self_collision (walk.yml:113) -> loadURDF
+        # flags, humanoid_stable_pd.py:10-13
+        dt = 1.0 / float(cfg.fps_sim)
+        if sim is None:
+            sim = SimParams(dt=dt, self_collision=bool(getattr(cfg, "self_collision", True)))
+        elif abs(sim.dt - dt) > 1e-12 * dt:
+            raise ValueError(f"SimParams.dt = {sim.dt} contradicts cfg.fps_sim = {cfg.fps_sim}: the window length "
+                             "(fps_sim // fps_act steps) and the stable-PD dt * Kd term both follow cfg.fps_sim")
         return cls(links, cfg.kps, cfg.kds, cfg.max_forces, np.asarray(cfg.joint_weights, dtype=np.float64),
                    list(cfg.end_effectors), np.asarray(cfg.cost_weights, dtype=np.float64), float(cfg.height),
                    sim, **kw)

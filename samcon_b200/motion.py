@@ -298,7 +298,7 @@ def _leg_ik(hip_org, knee_org, ankle_org, want, x0):
     return x
 
 
-def make_gait_motion(T=91, fr=30, seed=0, links=None, name=None, step_time=0.5, step_length=0.4, double_support=0.2,
+def make_gait_motion(T=91, fr=30, seed=0, links=None, name=None, step_time=0.6, step_length=0.36, double_support=0.25,
                      pelvis_height=0.93, half_width=0.09, sway=0.04, lift=0.06, ramp=0.3):
     """-> {name: {'fr': fr, 'pose': (T,75)}}: a walk built from footholds.
 
@@ -307,6 +307,10 @@ def make_gait_motion(T=91, fr=30, seed=0, links=None, name=None, step_time=0.5, 
     and a cycloidal swing to the next one; hip and knee angles come from inverse kinematics on the character's own
     link offsets, the ankle keeps the sole level.  Arms swing against the legs.  `seed` varies step length, cadence
     and sway by a few percent so that different seeds are different sequences.
+
+    Defaults (0.6 m/s): chosen inside the region where independent walk.yml-size searches (nSample 2000 / nSave 200) all
+    keep their best elite cost below ~2.5 for 30 windows on the B200 (profiles/r2a_gait_sweep.log; 0.4 m steps every
+    0.5 s still track at <= 4.1, 0.5 m steps or 0.4 s steps do not).
     """
     if links is None:
         from .urdf import load_links

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import abi
+from .abi import SC_CACHE_DIM as CACHE_DIM
 from .model import STATE_DIM, Character
 
 
@@ -49,6 +50,7 @@ class GpuSamplePool:
             self._h = None
             raise RuntimeError(f"sc_create failed ({rc}): {msg}")
         self._elites = None       # [E,132] device, parents of the next window
+        self._elite_cache = None  # [E,CACHE_DIM] device, their contact caches (None: empty caches)
         self._closed = False
 
     # ------------------------------------------------------------------ helpers
@@ -85,8 +87,24 @@ class GpuSamplePool:
         return {"smem_bytes": a.value, "samples_per_cta": b.value, "threads_per_cta": c.value}
 
     # ------------------------------------------------------------------ device-level API (C ABI 1:1)
-    def window(self, parents, actions, targets, nsteps, children=None, parent_idx=None, sample_seq=None, out=None):
-        """One SamCon window for all samples.  Returns (state [S,132], cost [S], info [S,5]) on the device."""
+    def contact_stats(self, reset=True):
+        """(sample-sub-steps whose candidate contacts exceeded max_contacts, sample-sub-steps simulated) since the last
+        reset.  Synchronises the device."""
+        out = (C.c_int64 * 2)()
+        self._check(self._lib.sc_contact_stats(self._h, out, int(bool(reset))), "sc_contact_stats")
+        return int(out[0]), int(out[1])
+
+    def empty_cache(self, n):
+        """n contact-cache rows without contacts (ids -1, impulses 0)."""
+        c = torch.zeros((n, CACHE_DIM), device=self.device, dtype=torch.float32)
+        c[:, :CACHE_DIM // 2] = -1.0
+        return c
+
+    def window(self, parents, actions, targets, nsteps, children=None, parent_idx=None, sample_seq=None, out=None,
+               parent_cache=None, out_cache=None):
+        """One SamCon window for all samples.  Returns (state [S,132], cost [S], info [S,5]) on the device.
+        ``parent_cache`` [E,CACHE_DIM]: the parents' contact caches (None: empty); ``out_cache`` [S,CACHE_DIM] receives
+        every sample's cache at the end of the window (pass True to have it allocated; it is then a 4th return value)."""
         parents = self._f32(parents)
         actions = self._f32(actions)
         targets = self._f32(targets).reshape(-1, STATE_DIM)
@@ -106,18 +124,29 @@ class GpuSamplePool:
             out = (torch.empty((S, STATE_DIM), device=self.device, dtype=torch.float32),
                    torch.empty((S,), device=self.device, dtype=torch.float32),
                    torch.empty((S, 5), device=self.device, dtype=torch.float32))
-        rc = self._lib.sc_window(self._h, _ptr(parents), E, _ptr(parent_idx), int(children), _ptr(actions), _ptr(targets),
-                                 nseq, _ptr(sample_seq), S, int(nsteps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
-                                 self._stream())
+        if parent_cache is not None:
+            parent_cache = self._f32(parent_cache, (E, CACHE_DIM))
+        want_cache = out_cache is True
+        if want_cache:
+            out_cache = torch.empty((S, CACHE_DIM), device=self.device, dtype=torch.float32)
+        elif out_cache is not None and (tuple(out_cache.shape) != (S, CACHE_DIM) or out_cache.dtype != torch.float32
+                                        or not out_cache.is_contiguous() or out_cache.device != self.device):
+            raise ValueError("out_cache must be a contiguous float32 [S, CACHE_DIM] tensor on the pool's device")
+        rc = self._lib.sc_window(self._h, _ptr(parents), _ptr(parent_cache), E, _ptr(parent_idx), int(children), _ptr(actions),
+                                 _ptr(targets), nseq, _ptr(sample_seq), S, int(nsteps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                 _ptr(out_cache), self._stream())
         self._check(rc, "sc_window")
-        return out
+        return (*out, out_cache) if want_cache else out
 
-    def step(self, state, actions, nsteps):
-        """In-place env.step (no cost) on [S,132] device states."""
+    def step(self, state, actions, nsteps, cache=None):
+        """In-place env.step (no cost) on [S,132] device states; ``cache`` [S,CACHE_DIM] is updated in place too."""
         state = self._f32(state)
         actions = self._f32(actions)
-        self._check(self._lib.sc_step(self._h, _ptr(state), _ptr(actions), state.shape[0], int(nsteps), self._stream()),
-                    "sc_step")
+        if cache is not None and (tuple(cache.shape) != (state.shape[0], CACHE_DIM) or cache.dtype != torch.float32
+                                  or not cache.is_contiguous() or cache.device != self.device):
+            raise ValueError("cache must be a contiguous float32 [S, CACHE_DIM] tensor on the pool's device")
+        self._check(self._lib.sc_step(self._h, _ptr(state), _ptr(cache), _ptr(actions), state.shape[0], int(nsteps),
+                                      self._stream()), "sc_step")
         return state
 
     def cost(self, sim, kin):
@@ -130,17 +159,39 @@ class GpuSamplePool:
         return out
 
     def sample_gen(self, target, limits, S, noise=None, perm=None, gaussian=False, seed=0, window=0, out=None):
-        target = self._f32(target, (STATE_DIM,))
+        """SamCon.get_batch_action on the device.  ``target`` [132] (one sequence) or [Q,132]: Q sequences with S samples
+        each in one launch, rows [q S, (q+1) S) drawn from the Philox stream (seed + q, window)."""
+        target = self._f32(target).reshape(-1, STATE_DIM)
+        Q = target.shape[0]
         limits = self._f32(limits, (3 * self.nj,))
-        noise = self._f32(noise, (S, 3 * self.nj)) if noise is not None else None
+        noise = self._f32(noise, (Q * S, 3 * self.nj)) if noise is not None else None
         perm = self._i32(perm)
         if out is None:
-            out = torch.empty((S, self.act_dim), device=self.device, dtype=torch.float32)
-        elif tuple(out.shape) != (S, self.act_dim) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
-            raise ValueError("out must be a contiguous float32 [S, 4*nj] tensor on the pool's device")
-        rc = self._lib.sc_sample_gen(self._h, _ptr(target), _ptr(limits), _ptr(noise), _ptr(perm), int(bool(gaussian)),
+            out = torch.empty((Q * S, self.act_dim), device=self.device, dtype=torch.float32)
+        elif tuple(out.shape) != (Q * S, self.act_dim) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+            raise ValueError("out must be a contiguous float32 [Q*S, 4*nj] tensor on the pool's device")
+        rc = self._lib.sc_sample_gen(self._h, _ptr(target), Q, _ptr(limits), _ptr(noise), _ptr(perm), int(bool(gaussian)),
                                      C.c_uint64(int(seed)), C.c_uint64(int(window)), int(S), _ptr(out), self._stream())
         self._check(rc, "sc_sample_gen")
+        return out
+
+    def motion_states(self, motions, times):
+        """AmassMotionData.getSpecTimeState for all (sequence, time) pairs on the device.  ``motions``: list of
+        (pose (T,75) array, key-frame duration) or AmassMotionData objects; ``times``: seconds.  -> [Q, len(times), 132]."""
+        poses, offs, dts = [], [0], []
+        for m in motions:
+            pose, dur = (m._motion, m.keyFrameDuration()) if hasattr(m, "keyFrameDuration") else m
+            pose = np.asarray(pose, dtype=np.float64)
+            if pose.ndim != 2 or pose.shape[1] != 7 + 4 * self.nj:
+                raise ValueError("pose arrays must be (T, 7 + 4*nj)")
+            poses.append(pose); offs.append(offs[-1] + pose.shape[0]); dts.append(float(dur))
+        d_pose = torch.tensor(np.concatenate(poses), dtype=torch.float32, device=self.device)
+        d_off = torch.tensor(offs, dtype=torch.int32, device=self.device)
+        d_dt = torch.tensor(dts, dtype=torch.float64, device=self.device)
+        d_t = torch.tensor(np.asarray(times, dtype=np.float64).reshape(-1), dtype=torch.float64, device=self.device)
+        out = torch.empty((len(poses), d_t.shape[0], STATE_DIM), device=self.device, dtype=torch.float32)
+        self._check(self._lib.sc_motion_states(self._h, _ptr(d_pose), _ptr(d_off), _ptr(d_dt), len(poses), _ptr(d_t),
+                                               int(d_t.shape[0]), _ptr(out), self._stream()), "sc_motion_states")
         return out
 
     def select(self, cost, E, seg_offsets=None):
@@ -153,7 +204,7 @@ class GpuSamplePool:
         idx = torch.empty((nseg, E), device=self.device, dtype=torch.int32)
         ec = torch.empty((nseg, E), device=self.device, dtype=torch.float32)
         self._check(self._lib.sc_select(self._h, _ptr(cost), _ptr(seg_offsets), nseg, int(E), _ptr(idx), _ptr(ec),
-                                        self._stream()), "sc_select")
+                                        int(cost.shape[0]), self._stream()), "sc_select")
         return idx, ec
 
     def gather_rows(self, src, idx):
@@ -164,14 +215,27 @@ class GpuSamplePool:
                                              self._stream()), "sc_gather_rows")
         return out
 
+    def gather_rows_peer(self, peer_base, src_peer, src_row, width):
+        """Rows out of other GPUs' buffers (sc_gather_rows_peer): peer_base int64 [npeer] device addresses of [*,width]
+        float32 arrays mapped into this process, src_peer / src_row int32 [n]."""
+        src_peer, src_row = self._i32(src_peer).reshape(-1), self._i32(src_row).reshape(-1)
+        if peer_base.dtype != torch.int64 or peer_base.device != self.device:
+            raise ValueError("peer_base must be an int64 tensor on the pool's device")
+        out = torch.empty((src_row.shape[0], int(width)), device=self.device, dtype=torch.float32)
+        self._check(self._lib.sc_gather_rows_peer(self._h, _ptr(peer_base), _ptr(src_peer), _ptr(src_row), src_row.shape[0],
+                                                  int(width), _ptr(out), self._stream()), "sc_gather_rows_peer")
+        return out
+
     # ------------------------------------------------------------------ worker-protocol mirror (host arrays)
     def init(self, init_state, nSave=1):
         """("init", [iter0, uid0, init_state]) -- samcon.py:42-46: every elite slot starts from init_state."""
         s = self._f32(np.asarray(init_state, dtype=np.float64), (STATE_DIM,))
         self._elites = s.reshape(1, STATE_DIM).repeat(int(nSave), 1).contiguous()
+        self._elite_cache = None
 
-    def set_elites(self, states):
+    def set_elites(self, states, caches=None):
         self._elites = self._f32(states).reshape(-1, STATE_DIM).contiguous()
+        self._elite_cache = self._f32(caches).reshape(-1, CACHE_DIM).contiguous() if caches is not None else None
 
     @property
     def elites(self):
@@ -183,8 +247,9 @@ class GpuSamplePool:
             raise RuntimeError("init() must be called before sim()")
         if not isinstance(actions, torch.Tensor):
             actions = np.asarray(actions, dtype=np.float32)
-        st, cost, info = self.window(self._elites, actions, np.asarray(target_state, dtype=np.float32), nsteps)
-        self._last = (st, cost, info)
+        st, cost, info, cache = self.window(self._elites, actions, np.asarray(target_state, dtype=np.float32), nsteps,
+                                            parent_cache=self._elite_cache, out_cache=True)
+        self._last = (st, cost, info, cache)
         # device -> pinned host staging (allocated once per sample count), one synchronisation for the three results;
         # the widening to the reference's float64 happens on the device (a numpy astype of 1.4 M values costs more
         # than the extra 5.5 MB over PCIe)
@@ -204,7 +269,9 @@ class GpuSamplePool:
 
     def keep(self, elite_inds):
         """Make the samples picked by Trajectory.select the parents of the next window (state stays in HBM)."""
-        self._elites = self.gather_rows(self._last[0], np.asarray(elite_inds, dtype=np.int32))
+        idx = self._i32(np.asarray(elite_inds, dtype=np.int32))
+        self._elites = self.gather_rows(self._last[0], idx)
+        self._elite_cache = self.gather_rows(self._last[3], idx)      # the snapshot carries the contact cache
 
     def close(self):
         if not self._closed and self._h:

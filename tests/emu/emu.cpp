@@ -8,7 +8,8 @@
 extern "C" {
 int emu_window(const sc_model *m, const float *parents, int E, const int *parent_idx, int children,
                const float *actions, const float *targets, int nseq, const int *sample_seq, int S, int nsteps,
-               float *out_state, float *out_cost, float *out_info, char *err, int errlen) {
+               float *out_state, float *out_cost, float *out_info, const float *parent_cache, float *out_cache, char *err,
+               int errlen) {
     sc::Tables T;
     int rc = sc::build_tables(m, &T, err, errlen);
     if (rc) return rc;
@@ -21,6 +22,7 @@ int emu_window(const sc_model *m, const float *parents, int E, const int *parent
     a.parents = parents; a.parent_idx = parent_idx; a.children = children; a.actions = actions; a.targets = targets;
     a.tfeat = tfeat.data(); a.sample_seq = sample_seq; a.S = S; a.nsteps = nsteps;
     a.out_state = out_state; a.out_cost = out_cost; a.out_info = out_info;
+    a.parent_cache = parent_cache; a.out_cache = out_cache;
     for (int t0 = 0; t0 < S; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, a, t0, 0, 32);
     return 0;
 }

@@ -11,14 +11,17 @@ class OraclePool:
 
     def init(self, init_state, nSave=1):
         self._elites = np.repeat(np.asarray(init_state, dtype=np.float64)[None], nSave, axis=0)
+        self._cache = None
 
     def sim(self, target_state, actions, nsteps):
-        st, cost, info = self.o.window(self._elites, np.asarray(actions, np.float64), np.asarray(target_state, np.float64), nsteps)
-        self._last = (st, cost, info)
+        st, cost, info, cache = self.o.window(self._elites, np.asarray(actions, np.float64), np.asarray(target_state, np.float64),
+                                              nsteps, parent_cache=self._cache, return_cache=True)
+        self._last = (st, cost, info, cache)
         return st, cost, info
 
     def keep(self, elite_inds):
         self._elites = self._last[0][np.asarray(elite_inds)]
+        self._cache = self._last[3][np.asarray(elite_inds)]
 
     def close(self):
         pass
@@ -37,26 +40,42 @@ class OracleDevicePool:
 
     def sample_gen(self, target, limits, S, noise=None, perm=None, gaussian=False, seed=0, window=0, out=None):
         from samcon_b200.sampling import get_batch_action
-        rs = np.random.RandomState((int(seed) * 1000003 + int(window)) % (2 ** 31))
-        a = get_batch_action(np.asarray(target, np.float64), S, np.asarray(limits, np.float64), "gaussian" if gaussian else "uniform", rs)
+        tg = np.asarray(target, np.float64).reshape(-1, 132)
+        rows = []
+        for q in range(len(tg)):                      # sequence q draws from the stream (seed + q, window), like the device
+            rs = np.random.RandomState(((int(seed) + q) * 1000003 + int(window)) % (2 ** 31))
+            rows.append(get_batch_action(tg[q], S, np.asarray(limits, np.float64), "gaussian" if gaussian else "uniform", rs))
+        a = np.concatenate(rows)
         t = self.torch.tensor(a, dtype=self.torch.float32)
         if out is not None:
             out.copy_(t)
             return out
         return t
 
-    def window(self, parents, actions, targets, nsteps, children=None, parent_idx=None, sample_seq=None, out=None):
+    def window(self, parents, actions, targets, nsteps, children=None, parent_idx=None, sample_seq=None, out=None,
+               parent_cache=None, out_cache=None):
         P = np.asarray(parents, np.float64); A = np.asarray(actions, np.float64)
         T = np.asarray(targets, np.float64).reshape(-1, 132)
         S = len(A)
         pidx = np.asarray(parent_idx) if parent_idx is not None else np.arange(S) // (children or S // len(P))
         seq = np.asarray(sample_seq) if sample_seq is not None else np.zeros(S, int)
-        st = np.zeros((S, 132)); cost = np.zeros(S); info = np.zeros((S, 5))
+        st = np.zeros((S, 132)); cost = np.zeros(S); info = np.zeros((S, 5)); cache = np.zeros((S, self.o.cache_dim))
+        PC = np.asarray(parent_cache, np.float64) if parent_cache is not None else None
         for k in range(S):
-            s, c, i = self.o.window(P[pidx[k]][None], A[k][None], T[seq[k]], nsteps)
-            st[k], cost[k], info[k] = s[0], c[0], i[0]
+            s, c, i, cc = self.o.window(P[pidx[k]][None], A[k][None], T[seq[k]], nsteps,
+                                        parent_cache=PC[pidx[k]][None] if PC is not None else None, return_cache=True)
+            st[k], cost[k], info[k], cache[k] = s[0], c[0], i[0], cc[0]
         f = lambda x: self.torch.tensor(x, dtype=self.torch.float32)
-        return f(st), f(cost), f(info)
+        res = (f(st), f(cost), f(info))
+        if out is not None:                            # like the GPU pool: results land in the caller's tensors
+            for dst, src in zip(out, res):
+                dst.copy_(src)
+            res = tuple(out)
+        if out_cache is True:
+            return (*res, f(cache))
+        if out_cache is not None:
+            out_cache.copy_(f(cache))
+        return res
 
     def select(self, cost, E, seg_offsets=None):
         c = np.asarray(cost, np.float64).reshape(-1)

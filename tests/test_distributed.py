@@ -55,18 +55,20 @@ def _worker(rank, world, port, out):
         S = len(actions)
         S_loc, E_loc = S // world, E // world
         search = ShardedSearch(pool, S_loc, E, rank, world)
+        assert search.exchange == "all_to_all"                   # no symmetric memory on CPU tensors: the collective path
         f = lambda x: torch.tensor(x, dtype=torch.float32)
-        blk, ids, ecost, (st, cost, info) = search.window(f(parents[rank * E_loc:(rank + 1) * E_loc]),
-                                                          f(actions[rank * S_loc:(rank + 1) * S_loc]), f(target), 15)
-        # second window from the exchanged elites: every rank must hold the same elite table
-        elites, ids2, _ = search.select_and_exchange(st, cost)
-        out[rank] = (blk.numpy(), ids.numpy(), ecost.numpy(), elites.numpy())
+        acts = f(actions[rank * S_loc:(rank + 1) * S_loc])
+        blk, bcache, ids, ecost, _ = search.window(f(parents[rank * E_loc:(rank + 1) * E_loc]), acts, f(target), 15)
+        # second window from the exchanged parent block, contact caches included
+        blk2, bcache2, ids2, ecost2, _ = search.window(blk, acts, f(target), 15, parent_cache=bcache)
+        out[rank] = (blk.numpy(), bcache.numpy(), ids.numpy(), ecost.numpy(), blk2.numpy(), bcache2.numpy(), ids2.numpy(), ecost2.numpy())
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
 def test_two_rank_search_equals_unsharded():
+    """Two chained windows on 2 ranks == the same two windows on one: elite ids, costs, parent states and contact caches."""
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
@@ -74,14 +76,56 @@ def test_two_rank_search_equals_unsharded():
     pool = _make_pool()
     parents, actions, target, E, children = _inputs()
     f = lambda x: torch.tensor(x, dtype=torch.float32)
-    st, cost, info = pool.window(f(parents), f(actions), f(target), 15)
+    E_loc = E // world
+    st, cost, info, cache = pool.window(f(parents), f(actions), f(target), 15, out_cache=True)
     idx, ec = pool.select(cost, E)
-    ref_ids = idx[0].numpy()
-    ref_states = st[idx[0].long()].numpy()
+    ref_ids, ref_states, ref_cache = idx[0].numpy(), st[idx[0].long()], cache[idx[0].long()]
+    st2, cost2, _, cache2 = pool.window(ref_states, f(actions), f(target), 15, parent_cache=ref_cache, out_cache=True)
+    idx2, ec2 = pool.select(cost2, E)
+    assert (ref_cache[:, 0] >= 0).any()                          # the scenario does carry contacts across the windows
     for r in range(world):
-        blk, ids, ecost, elites = out[r]
+        blk, bcache, ids, ecost, blk2, bcache2, ids2, ecost2 = out[r]
         assert list(ids) == list(ref_ids)                        # global sample ids of the elites, ascending cost
         np.testing.assert_array_equal(ecost, ec[0].numpy())
-        np.testing.assert_array_equal(elites, ref_states)        # x + 0 exchange is exact
-        np.testing.assert_array_equal(blk, ref_states[r * (E // world):(r + 1) * (E // world)])
-    np.testing.assert_array_equal(out[0][3], out[1][3])
+        np.testing.assert_array_equal(blk, ref_states[r * E_loc:(r + 1) * E_loc].numpy())      # x + 0 exchange is exact
+        np.testing.assert_array_equal(bcache, ref_cache[r * E_loc:(r + 1) * E_loc].numpy())
+        assert list(ids2) == list(idx2[0].numpy())
+        np.testing.assert_array_equal(ecost2, ec2[0].numpy())
+        np.testing.assert_array_equal(blk2, st2[idx2[0].long()][r * E_loc:(r + 1) * E_loc].numpy())
+        np.testing.assert_array_equal(bcache2, cache2[idx2[0].long()][r * E_loc:(r + 1) * E_loc].numpy())
+
+
+def _seq_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from samcon_b200.config import Config
+        from samcon_b200.distributed import solve_sequences_sharded
+        from samcon_b200.motion import AmassMotionData, make_synthetic_motion
+        loaders = []
+        for seed in (0, 1, 2):
+            m = make_synthetic_motion("gait", T=12, seed=seed)
+            (name, _), = m.items()
+            loaders.append(AmassMotionData(m, name))
+        q0, res = solve_sequences_sharded(Config("walk"), loaders, _make_pool(), rank, world, nIter=2, nSample=6, nSave=2)
+        out[rank] = (q0, [(r["total_cost"], r["action"]) for r in res])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sequences_sharded_over_ranks():
+    """Config 5 on N ranks: sequences are dealt to the ranks in blocks, no collective; every sequence gets the result it
+    gets when all are solved by one rank (its Philox stream is keyed by its global index)."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_seq_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    one = mgr.dict()
+    mp.spawn(_seq_worker, args=(1, _free_port(), one), nprocs=1, join=True)
+    assert out[0][0] == 0 and out[1][0] == 2 and len(out[0][1]) == 2 and len(out[1][1]) == 1
+    both = out[0][1] + out[1][1]
+    for (c, a), (c1, a1) in zip(both, one[0][1]):
+        assert c == c1
+        np.testing.assert_array_equal(a, a1)

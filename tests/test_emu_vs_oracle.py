@@ -24,7 +24,8 @@ def emu():
     return C.CDLL(lib)
 
 
-def _window(emu, character, parents, actions, targets, nsteps, children=1, parent_idx=None, sample_seq=None):
+def _window(emu, character, parents, actions, targets, nsteps, children=1, parent_idx=None, sample_seq=None,
+            parent_cache=None, return_cache=False):
     m, keep = make_model(character)
     parents = np.ascontiguousarray(parents, np.float32)
     actions = np.ascontiguousarray(actions, np.float32)
@@ -39,10 +40,12 @@ def _window(emu, character, parents, actions, targets, nsteps, children=1, paren
         return a.ctypes.data_as(C.c_void_p) if a is not None else None
     pi = np.ascontiguousarray(parent_idx, np.int32) if parent_idx is not None else None
     sq = np.ascontiguousarray(sample_seq, np.int32) if sample_seq is not None else None
+    pc = np.ascontiguousarray(parent_cache, np.float32) if parent_cache is not None else None
+    oc = np.zeros((S, 16), np.float32) if return_cache else None
     rc = emu.emu_window(C.byref(m), p(parents), E, p(pi), children, p(actions), p(targets), len(targets), p(sq), S, nsteps,
-                        p(st), p(cost), p(info), err, 256)
+                        p(st), p(cost), p(info), p(pc), p(oc), err, 256)
     assert rc == 0, err.value
-    return st, cost, info
+    return (st, cost, info, oc) if return_cache else (st, cost, info)
 
 
 def test_airborne(emu, character, oracle):
@@ -143,3 +146,51 @@ def test_contact_cap_paths(emu, character, oracle):
     ost, ocost, _ = oracle.window(parents, actions, target, 6)
     assert joint_rms(st, ost).max() < 2e-4
     np.testing.assert_allclose(st[:, :3], ost[:, :3], atol=1e-4)
+
+
+def test_contact_cache_chain(emu, character, oracle):
+    """The contact cache is part of a sample's state: a window cut in two and resumed from (state, cache) gives the
+    bits of the uncut window (that is what restoring a .bullet snapshot does for the reference,
+    humanoid_tracking_env.py:178-182); resumed from the state alone it does not.  The cache rows agree with the oracle's."""
+    rng = np.random.default_rng(11)
+    parents = np.array([stand(rng, 0.05, 0.2, 0.98 + 0.005 * i) for i in range(6)])
+    actions = np.array([near_action(p, rng, 0.1) for p in parents])
+    target = stand(rng)
+    full, cfull, _, cache_full = _window(emu, character, parents, actions, target, 100, return_cache=True)
+    half, _, _, cache_half = _window(emu, character, parents, actions, target, 50, return_cache=True)
+    assert (cache_half[:, 0] >= 0).sum() >= 4 and (cache_half[:, 8:] >= 0).all() and cache_half[:, 8:].max() > 0.01
+    rest, crest, _, cache_rest = _window(emu, character, half, actions, target, 50, parent_cache=cache_half, return_cache=True)
+    np.testing.assert_array_equal(rest, full)
+    np.testing.assert_array_equal(crest, cfull)
+    np.testing.assert_array_equal(cache_rest, cache_full)
+    cold, _, _ = _window(emu, character, half, actions, target, 50)
+    assert np.abs(cold - full).max() > 0                                          # the cache matters
+    # against the oracle: same candidate ids in the same slots, impulses to float accuracy; and the same chain
+    ost, ocost, _, ocache = oracle.window(parents, actions, target, 50, return_cache=True)
+    np.testing.assert_array_equal(cache_half[:, :8], ocache[:, :8])
+    # (how a foot's load splits over its corners is ill-conditioned; the total is not)
+    np.testing.assert_allclose(cache_half[:, 8:], ocache[:, 8:], rtol=0.1, atol=1e-3)
+    np.testing.assert_allclose(cache_half[:, 8:].sum(1), ocache[:, 8:].sum(1), rtol=5e-2, atol=1e-4)      # one sub-step's impulse of a settling contact is noisy
+    ost2, ocost2, _ = oracle.window(ost, actions, target, 50, parent_cache=ocache)
+    ofull, ocfull, _ = oracle.window(parents, actions, target, 100)
+    np.testing.assert_array_equal(ost2, ofull)
+    assert joint_rms(rest, ost2).max() < 1e-3
+
+
+def test_warmstart_off_matches_stateless_oracle(emu, walk_cfg):
+    """warmstart = 0 is the round-1 stateless contact model, on both sides."""
+    from oracle.oracle import Oracle
+    from samcon_b200.model import Character, SimParams
+    ch = Character.from_config(walk_cfg, SimParams(warmstart=0.0))
+    o = Oracle(ch)
+    rng = np.random.default_rng(12)
+    parents = np.array([stand(rng, 0.05, 0.2, 0.98 + 0.005 * i) for i in range(4)])
+    actions = np.array([near_action(p, rng, 0.1) for p in parents])
+    target = stand(rng)
+    st, cost, _, cache = _window(emu, ch, parents, actions, target, 60, return_cache=True)
+    ost, ocost, _ = o.window(parents, actions, target, 60)
+    assert joint_rms(st, ost).max() < 1e-3
+    np.testing.assert_allclose(cost, ocost, rtol=1e-3)
+    again, _, _ = _window(emu, ch, st, actions, target, 20, parent_cache=cache)
+    cold, _, _ = _window(emu, ch, st, actions, target, 20)
+    np.testing.assert_array_equal(again, cold)                                      # without warm start the cache is inert

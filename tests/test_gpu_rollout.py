@@ -147,13 +147,104 @@ def test_self_contact_window(pool, oracle):
 
 def test_committed_fixture_windows(pool):
     """The committed oracle fixtures (tests/golden/oracle_windows.npz) through the C ABI: the GPU path against
-    numbers that travel with the repo (the walk-cfg scenarios; the pool is built from walk.yml)."""
+    numbers that travel with the repo -- the walk-cfg scenarios on the walk.yml pool, the cartwheel hand stand on a pool
+    built from cartwheel.yml (its own cost weights)."""
     import os
+    from samcon_b200.config import Config
+    from samcon_b200.model import Character
+    from samcon_b200.pool import GpuSamplePool
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_windows.npz"))
     for key in ("air", "stand", "self"):
         st, cost, info = _run(pool, g[f"{key}_parents"], g[f"{key}_actions"], g[f"{key}_target"], int(g[f"{key}_nsteps"]), 1)
         assert joint_rms(st, g[f"{key}_state"]).max() < JOINT_TOL
         np.testing.assert_allclose(cost, g[f"{key}_cost"], rtol=COST_RTOL)
+    cw = GpuSamplePool(Character.from_config(Config("cartwheel")), 0)
+    try:
+        key = "cartwheel"
+        st, cost, info = _run(cw, g[f"{key}_parents"], g[f"{key}_actions"], g[f"{key}_target"], int(g[f"{key}_nsteps"]), 1)
+        rms = joint_rms(st, g[f"{key}_state"])
+        print(f"cartwheel fixture: joint rms {rms}, cost {cost} vs {g[f'{key}_cost']}")
+        assert rms.max() < JOINT_TOL
+        np.testing.assert_allclose(cost, g[f"{key}_cost"], rtol=COST_RTOL)
+    finally:
+        cw.close()
+
+
+def test_contact_cache_travels_with_the_state(pool, oracle):
+    """Warm-started contacts: the cache row is part of a sample's state.  (i) A window cut in two and resumed from
+    (state, cache) is the uncut window bit for bit -- what restoring a .bullet snapshot gives the reference
+    (humanoid_tracking_env.py:178-182); resumed from the state alone it is not.  (ii) Cache rows: the oracle's candidate
+    ids in the oracle's slots.  (iii) A chain of windows through pool.sim/keep (which carries the caches) agrees with the
+    oracle chained the same way."""
+    import torch
+    rng = np.random.default_rng(21)
+    parents = np.array([stand(rng, 0.05, 0.2, 0.98 + 0.004 * i) for i in range(12)]).astype(np.float32)
+    actions = np.array([near_action(p, rng, 0.1) for p in parents]).astype(np.float32)
+    target = stand(rng).astype(np.float32)
+    full = pool.window(parents, actions, target, 100, children=1, out_cache=True)
+    half = pool.window(parents, actions, target, 50, children=1, out_cache=True)
+    rest = pool.window(half[0], actions, target, 50, children=1, parent_cache=half[3], out_cache=True)
+    for a, b in zip(full, rest):
+        assert torch.equal(a, b)
+    cold = pool.window(half[0], actions, target, 50, children=1)
+    assert not torch.equal(cold[0], full[0])
+    ost, ocost, _, ocache = oracle.window(parents, actions, target, 50, return_cache=True)
+    hc = half[3].cpu().numpy()
+    assert (hc[:, 0] >= 0).sum() >= 8
+    np.testing.assert_array_equal(hc[:, :8], ocache[:, :8])
+    np.testing.assert_allclose(hc[:, 8:].sum(1), ocache[:, 8:].sum(1), rtol=5e-2, atol=1e-4)
+    ost2, ocost2, _ = oracle.window(ost, actions, target, 50, parent_cache=ocache)
+    assert joint_rms(rest[0].cpu().numpy(), ost2).max() < JOINT_TOL
+    np.testing.assert_allclose(rest[1].cpu().numpy(), ocost2, rtol=COST_RTOL)
+    # (iii) host protocol: init / sim / keep
+    from oracle_pool import OraclePool
+    op = OraclePool(oracle)
+    E, children = 4, 3
+    pool.init(parents[0], E); op.init(parents[0], E)
+    acts = np.array([near_action(parents[0], rng, 0.08) for _ in range(E * children)])
+    for w in range(3):
+        gs, gc, gi = pool.sim(target, acts.astype(np.float32), 40)
+        os_, oc, oi = op.sim(target, acts.astype(np.float32), 40)
+        assert joint_rms(gs, os_).max() < JOINT_TOL
+        np.testing.assert_allclose(gc, oc, rtol=COST_RTOL)
+        keep = np.lexsort((np.arange(len(oc)), oc))[:E]
+        pool.keep(keep); op.keep(keep)
+
+
+def test_contact_cap_statistics(pool):
+    """sc_contact_stats: how often more candidate points were inside the margin than max_contacts.  A humanoid lying on
+    the ground overflows in every sub-step, an airborne one never."""
+    rng = np.random.default_rng(22)
+    pool.contact_stats(reset=True)
+    air = np.array([rand_state(rng, 0.3, 3.0) for _ in range(5)]).astype(np.float32)
+    pool.window(air, air[:, 7:75].copy(), air[0], 10, children=1)
+    ov, n = pool.contact_stats()
+    assert (ov, n) == (0, 5 * 10 * 2)
+    lying = stand(rng, 0.02, 0.0, 0.08)
+    lying[3:7] = [0, 0, 0, 1]
+    lying = np.repeat(lying[None], 3, axis=0).astype(np.float32)
+    pool.window(lying, lying[:, 7:75].copy(), lying[0], 10, children=1)
+    ov, n = pool.contact_stats()
+    assert n == 3 * 10 * 2 and ov >= n // 2
+    assert pool.contact_stats() == (0, 0)
+
+
+def test_entry_points_restore_the_callers_device(character):
+    """Every C-ABI call runs on the handle's device and puts the caller's current device back."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from samcon_b200.pool import GpuSamplePool
+    other = GpuSamplePool(character, 1)
+    try:
+        assert torch.cuda.current_device() == 0
+        rng = np.random.default_rng(23)
+        p = torch.tensor(np.array([stand(rng) for _ in range(2)]), dtype=torch.float32, device="cuda:1")
+        other.window(p, p[:, 7:75].contiguous(), p[0], 5, children=1)
+        other.select(torch.rand(100, device="cuda:1"), 10)
+        assert torch.cuda.current_device() == 0
+    finally:
+        other.close()
 
 
 def test_select_edge_cases(pool):
@@ -168,6 +259,9 @@ def test_select_edge_cases(pool):
     idx, ec = pool.select(c, 4, seg_offsets=seg)
     assert idx.tolist() == [[1, 0, 2, -1], [3, -1, -1, -1], [7, 5, 6, 4]]
     assert ec[0, 3] == float("inf") and ec[1, 1] == float("inf")
+    # a padded result is safe to gather with: -1 gives a zero row
+    rows = pool.gather_rows(torch.arange(16, dtype=torch.float32, device="cuda").reshape(8, 2), idx[1])
+    assert rows.tolist() == [[6.0, 7.0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0]]
     # bad arguments come back as errors, not launches
     with pytest.raises(RuntimeError, match="sc_select"):
         pool.select(c, 0)

@@ -137,14 +137,21 @@ def test_batched_multi_sequence_equals_single_runs(oracle):
         for key in ("simulated_state", "action", "cost", "elite_cost", "target_state"):
             np.testing.assert_array_equal(alone[key], both[q][key])
         assert alone["total_cost"] == both[q]["total_cost"]
-    # elite costs ascend, the best path ends in the cheapest elite of the last window
+    # elite costs ascend; the best path is the cheapest of the nSave back-traced paths (trajectory.py:125-148), which
+    # need not end in the cheapest elite of the last window
     assert (np.diff(both[0]["elite_cost"], axis=1) >= 0).all()
-    assert both[0]["cost"][-1] == both[0]["elite_cost"][-1, 0]
-    # Q = 1 with host noise is the reference loop: same elites as SamCon on the same pool arithmetic
+    assert both[0]["total_cost"] == both[0]["path_total_costs"].min()
+    # Q = 1 with host noise is the reference loop: same best path as SamCon / Trajectory.find_paths on the same pool
+    # arithmetic (the batched pool stores float32 rows, hence the tolerance), over enough windows for paths to cross
+    kw = dict(nIter=4, nSample=12, nSave=3)
+    one = BatchedSamCon(cfg, [loaders[0]], pool, device_noise=False, **kw).sample()[0]
     cfg.motion_seq = "x"
-    ref = SamCon(cfg, loaders[0], 1, 2, 12, 3, pool=OraclePool(oracle))
+    ref = SamCon(cfg, loaders[0], 1, 4, 12, 3, pool=OraclePool(oracle))
     out, info = ref.sample(save=False)
-    np.testing.assert_allclose(out["x"]["path_0"]["cost"].reshape(-1), both[0]["cost"], rtol=1e-5)
+    np.testing.assert_allclose(out["x"]["path_0"]["cost"].reshape(-1), one["cost"], rtol=1e-4)
+    np.testing.assert_allclose(out["x"]["path_0"]["total_cost"], one["total_cost"], rtol=1e-4)
+    np.testing.assert_allclose(out["x"]["path_0"]["action"], one["action"], atol=1e-6)
+    np.testing.assert_allclose(sorted(out["x"][f"path_{i}"]["total_cost"] for i in range(3)), np.sort(one["path_total_costs"]), rtol=1e-4)
 
 
 def test_result_pickles_have_the_reference_layout(oracle, motion, tmp_path):

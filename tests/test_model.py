@@ -81,3 +81,28 @@ def test_inertia_models(character):
 def test_character_validation(walk_cfg):
     with pytest.raises(ValueError):
         Character(load_links(None), np.ones(16), np.ones(17), np.ones(17), np.ones(17), [14, 18, 2, 5], np.ones(5), 1.65)
+
+
+def test_time_step_follows_cfg_fps_sim(walk_cfg):
+    """setTimeStep(1 / cfg.fps_sim) (humanoid_tracking_env.py:25, 46): the character built from a cfg simulates at the
+    cfg's rate (it used to keep the 1 ms default), and a contradicting explicit SimParams is refused."""
+    import copy
+    import numpy as np
+    import pytest
+    from helpers import near_action, stand
+    from oracle.oracle import Oracle
+    from samcon_b200.model import Character, SimParams
+    cfg = copy.copy(walk_cfg)
+    cfg.fps_sim = 500
+    ch = Character.from_config(cfg)
+    assert abs(ch.sim.dt - 1.0 / 500) < 1e-15
+    with pytest.raises(ValueError, match="fps_sim"):
+        Character.from_config(cfg, SimParams())                   # dt = 1/1000 against fps_sim = 500
+    assert Character.from_config(cfg, SimParams(dt=1.0 / 500)).sim.dt == 1.0 / 500
+    # 50 steps at 500 Hz and 100 steps at 1000 Hz cover the same 0.1 s: a free fall ends at the same height
+    rng = np.random.default_rng(0)
+    s = stand(rng, 0.0, 0.0, 3.0)
+    a = near_action(s, rng, 0.0)
+    z500 = Oracle(ch).step(s, a, 50)[2]
+    z1000 = Oracle(Character.from_config(walk_cfg)).step(s, a, 100)[2]
+    assert abs((3.0 - z500) - 0.5 * 9.8 * 0.01) < 2e-3 and abs(z500 - z1000) < 5e-4      # semi-implicit Euler: O(dt) apart

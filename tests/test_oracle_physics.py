@@ -47,8 +47,11 @@ def test_momentum_error_is_first_order_in_dt(walk_cfg):
     from samcon_b200.model import Character, SimParams
     from oracle.oracle import Oracle
     errs = []
+    import copy
     for dt, n in ((1e-3, 400), (5e-4, 800)):
-        o = Oracle(Character.from_config(walk_cfg, SimParams(dt=dt)))
+        cfg = copy.copy(walk_cfg)
+        cfg.fps_sim = round(1.0 / dt)                                # the time step is the cfg's (setTimeStep(1/fps_sim))
+        o = Oracle(Character.from_config(cfg))
         s = rand_state(np.random.default_rng(5), 1.0, 5.0)
         _, _, _, v0 = o.link_coms(s)
         _, _, _, v1 = o.link_coms(o.step_torque(s, np.zeros(57), n))
@@ -219,10 +222,11 @@ def test_standing_ground_reaction_carries_the_weight(oracle, character):
     s = stand(rng, 0.0, 0.0, 0.99)
     s[0:2] = 0
     a = s[7:75].copy()
-    s = oracle.step(s, a, 400)
+    cache = oracle.empty_cache()            # the contact cache travels with the state from call to call
+    s = oracle.step(s, a, 400, cache)
     imp = []
     for _ in range(100):
-        s = oracle.step(s, a, 1)
+        s = oracle.step(s, a, 1, cache)
         imp.append(oracle.last_ground_impulse())
     imp = np.array(imp)
     h = character.sim.dt / character.sim.num_substeps

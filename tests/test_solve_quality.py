@@ -34,10 +34,10 @@ def test_gait_is_kinematically_consistent(character):
         p = ld._motion[f].copy(); z0 = p[2]; p[2] = 0.0
         assert z0 + _lowest_point(character.links, p) > -2e-3
     feet = np.array(feet)                                          # [T, 2, 3]
-    low = feet[:, :, 2].min()
     for k in range(2):
-        on_ground = feet[:, k, 2] < low + 2e-3
-        assert on_ground.sum() > 0.5 * len(feet)
+        low = feet[:, k, 2].min()
+        on_ground = feet[:, k, 2] < low + 1e-4
+        assert on_ground.sum() > 0.4 * len(feet)
         # consecutive grounded frames: the foot does not slide
         d = np.linalg.norm(np.diff(feet[:, k, :2], axis=0), axis=1)[on_ground[1:] & on_ground[:-1]]
         assert d.max() < 1e-6
