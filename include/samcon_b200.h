@@ -105,19 +105,22 @@ int sc_motion_states(sc_handle h, const float *poses, const int32_t *frame_offse
  * [E,SC_CACHE_DIM] is restored with it; NULL = empty caches, the first window), holds actions[k] for nsteps x {stable PD;
  * stepSimulation}, and is scored against targets[sample_seq ? sample_seq[k] : 0].  Outputs in sample order: out_state
  * [S,132], out_cost [S], out_info [S,5] = pose, root, ee, balance, com, out_cache [S,SC_CACHE_DIM] (save_pb_state,
- * humanoid_tracking_env.py:178-179); any output may be NULL. */
+ * humanoid_tracking_env.py:178-179), out_overflow [S] = in how many of the window's sub-steps the sample had more than
+ * max_contacts candidate points inside the margin (low 16 bits) / touching (high 16 bits), see sc_contact_stats; any output
+ * may be NULL. */
 int sc_window(sc_handle h, const float *parents, const float *parent_cache, int E, const int32_t *parent_idx, int children,
               const float *actions, const float *targets, int nseq, const int32_t *sample_seq, int S, int nsteps,
-              float *out_state, float *out_cost, float *out_info, float *out_cache, void *stream);
+              float *out_state, float *out_cost, float *out_info, float *out_cache, int32_t *out_overflow, void *stream);
 
 /* env.step without the cost: used by the replay facade (scripts/eval_samcon.py:67-81). state [S,132] and cache
  * [S,SC_CACHE_DIM] (or NULL: empty caches in, result dropped) are updated in place. */
 int sc_step(sc_handle h, float *state, float *cache, const float *actions, int S, int nsteps, void *stream);
 
-/* Diagnostic, SYNCHRONISES the device: out2[0] = sample-sub-steps in which more candidate points were inside the contact
- * margin than max_contacts (the deepest were kept), out2[1] = sample-sub-steps simulated by sc_window / sc_step since the
- * handle was created or last reset. */
-int sc_contact_stats(sc_handle h, int64_t *out2, int reset);
+/* Diagnostic, SYNCHRONISES the device.  out3[0] = sample-sub-steps in which more candidate points were inside the contact
+ * margin than max_contacts (the deepest were kept: what is dropped first are speculative points that do not touch yet),
+ * out3[1] = sample-sub-steps simulated by sc_window / sc_step since the handle was created or last reset, out3[2] = sample-
+ * sub-steps in which more than max_contacts points were actually TOUCHING (distance <= 0), i.e. a live contact was dropped. */
+int sc_contact_stats(sc_handle h, int64_t *out3, int reset);
 
 /* compute_total_cost for explicit (sim, kin) pairs -- humanoid_tracking_env.py:78-90. out [S,6] total + 5 terms */
 int sc_cost(sc_handle h, const float *sim, const float *kin, int S, float *out, void *stream);

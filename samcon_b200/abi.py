@@ -106,7 +106,7 @@ def load():
     lib.sc_last_error.restype = C.c_char_p
     lib.sc_sample_gen.argtypes = [vp, vp, i, vp, vp, vp, i, u64, u64, i, vp, vp]
     lib.sc_motion_states.argtypes = [vp, vp, vp, vp, i, vp, i, vp, vp]
-    lib.sc_window.argtypes = [vp, vp, vp, i, vp, i, vp, vp, i, vp, i, i, vp, vp, vp, vp, vp]
+    lib.sc_window.argtypes = [vp, vp, vp, i, vp, i, vp, vp, i, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.sc_step.argtypes = [vp, vp, vp, vp, i, i, vp]
     lib.sc_contact_stats.argtypes = [vp, C.POINTER(C.c_int64), i]
     lib.sc_cost.argtypes = [vp, vp, vp, i, vp, vp]

@@ -71,45 +71,61 @@ class BatchedSamCon:
                                                 self._rngs[q]) for q in range(Q)])
         return torch.tensor(host, dtype=torch.float32, device=self._pool.device)
 
+    def begin(self):
+        """Every elite slot of every sequence = the sequence's t0 state, empty contact caches, no history."""
+        self._parents = self._targets[:, 0, :].repeat_interleave(self.E, dim=0).contiguous()
+        self._pcache = None
+        self._hist = []
+
+    def step(self, t):
+        """Window t (1-based) for all sequences: ONE sample_gen, ONE rollout, ONE segmented select, gathers.  Nothing
+        returns to the host.  -> elite costs [Q,E] (device)."""
+        pool, Q, S, E = self._pool, self.Q, self.S, self.E
+        act = self._actions(t)
+        st, cost, info, cache = pool.window(self._parents, act, self._targets[:, t, :].contiguous(), self.steps,
+                                            parent_idx=self._parent_idx, sample_seq=self._sample_seq,
+                                            parent_cache=self._pcache, out_cache=True)
+        idx, ecost = pool.select(cost, E, seg_offsets=self._seg)                           # [Q,E] global sample ids
+        flat = idx.reshape(-1)
+        self._parents = pool.gather_rows(st, flat)
+        self._pcache = pool.gather_rows(cache, flat)                                       # the snapshot carries the contact cache
+        eact = pool.gather_rows(act, flat)
+        eparent = (flat.to(torch.int64) % S) // self.children                             # elite slot of window t-1
+        self._hist.append((self._parents, eact, ecost, eparent.reshape(Q, E)))
+        return ecost
+
     def sample(self):
         """Run all windows.  Returns a list (one per sequence) of dicts with the reference's per-path arrays for the
         best path: ``simulated_state`` (nIter,132), ``action`` (nIter,68), ``cost`` (nIter,), ``target_state``
         (nIter,132), ``t0_state`` (132,), ``total_cost``; plus ``elite_cost`` (nIter, nSave)."""
-        pool, Q, S, E = self._pool, self.Q, self.S, self.E
-        parents = self._targets[:, 0, :].repeat_interleave(E, dim=0).contiguous()          # every elite slot = t0 state
-        pcache = None                                                                      # contact caches of the parents
-        hist = []
+        self.begin()
         for t in range(1, self.nIter + 1):
-            act = self._actions(t)
-            st, cost, info, cache = pool.window(parents, act, self._targets[:, t, :].contiguous(), self.steps,
-                                                parent_idx=self._parent_idx, sample_seq=self._sample_seq,
-                                                parent_cache=pcache, out_cache=True)
-            idx, ecost = pool.select(cost, E, seg_offsets=self._seg)                       # [Q,E] global sample ids
-            flat = idx.reshape(-1)
-            parents = pool.gather_rows(st, flat)
-            pcache = pool.gather_rows(cache, flat)
-            eact = pool.gather_rows(act, flat)
-            eparent = (flat.to(torch.int64) % S) // self.children                         # elite slot of window t-1
-            hist.append((parents, eact, ecost, eparent.reshape(Q, E)))
+            self.step(t)
+        return self.finish()
+
+    def finish(self):
+        Q, E = self.Q, self.E
+        hist = self._hist
+        nW = len(hist)                                             # windows stepped so far (nIter for a full solve)
         # ---- best path per sequence (trajectory.py:118-154): back-trace every elite of the last window through the
         # stored parent slots, sum the cost along each path, take the cheapest (stable ties, like find_paths' argsort)
         H = [(p.reshape(Q, E, STATE_DIM).cpu().numpy().astype(np.float64), a.reshape(Q, E, -1).cpu().numpy().astype(np.float64),
               c.cpu().numpy().astype(np.float64), e.cpu().numpy()) for p, a, c, e in hist]
         out = []
         for q in range(Q):
-            slots = np.zeros((self.nIter, E), dtype=np.int64)          # slots[t, j]: elite slot of path j in window t+1
+            slots = np.zeros((nW, E), dtype=np.int64)          # slots[t, j]: elite slot of path j in window t+1
             slots[-1] = np.arange(E)
-            for t in range(self.nIter - 1, 0, -1):
+            for t in range(nW - 1, 0, -1):
                 slots[t - 1] = H[t][3][q, slots[t]]
             total = np.zeros(E)
-            for t in range(self.nIter):
+            for t in range(nW):
                 total += H[t][2][q, slots[t]]
             j = int(np.argsort(total, kind="stable")[0])
-            sim = [H[t][0][q, slots[t, j]] for t in range(self.nIter)]
-            acts = [H[t][1][q, slots[t, j]] for t in range(self.nIter)]
-            costs = [H[t][2][q, slots[t, j]] for t in range(self.nIter)]
+            sim = [H[t][0][q, slots[t, j]] for t in range(nW)]
+            acts = [H[t][1][q, slots[t, j]] for t in range(nW)]
+            costs = [H[t][2][q, slots[t, j]] for t in range(nW)]
             out.append({"simulated_state": np.array(sim), "action": np.array(acts), "cost": np.array(costs),
-                        "target_state": self.targets_host[q, 1:], "t0_state": self.targets_host[q, 0],
+                        "target_state": self.targets_host[q, 1:nW + 1], "t0_state": self.targets_host[q, 0],
                         "total_cost": float(np.sum(costs)), "elite_cost": np.stack([h[2][q] for h in H]),
                         "path_total_costs": total})
         return out

@@ -27,7 +27,9 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    if not force and not _stale():
+    # (on a box without nvcc -- never the case in this image -- a prebuilt library is used as it is)
+    nvcc_path = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+    if (not force and not _stale()) or (not os.path.exists(nvcc_path) and os.path.exists(LIB)):
         return LIB
     nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(_CSRC, s) for s in SOURCES]]

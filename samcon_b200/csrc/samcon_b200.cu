@@ -438,7 +438,7 @@ struct sc_context {
     int smem_bytes, grid_cap;
     long long launches;
     long long *d_prof;
-    unsigned long long *d_stats;    // [2] contact statistics, see sc_contact_stats
+    unsigned long long *d_stats;    // [3] contact statistics, see sc_contact_stats
     char err[512];
 };
 
@@ -464,8 +464,8 @@ extern "C" int sc_create(sc_handle *out, const sc_model *model, int device) {
     int rc = build_tables(model, &h->h_tables, h->err, sizeof h->err);
     if (rc) return rc;
     SC_ON_DEVICE(h);
-    SC_CUDA(h, cudaMalloc(&h->d_stats, 2 * sizeof(unsigned long long)));
-    SC_CUDA(h, cudaMemset(h->d_stats, 0, 2 * sizeof(unsigned long long)));
+    SC_CUDA(h, cudaMalloc(&h->d_stats, 3 * sizeof(unsigned long long)));
+    SC_CUDA(h, cudaMemset(h->d_stats, 0, 3 * sizeof(unsigned long long)));
     SC_CUDA(h, cudaMalloc(&h->d_tables, TABLE_WORDS * 4));
     SC_CUDA(h, cudaMemset(h->d_tables, 0, TABLE_WORDS * 4));
     SC_CUDA(h, cudaMemcpy(h->d_tables, &h->h_tables, sizeof(Tables), cudaMemcpyHostToDevice));
@@ -494,12 +494,12 @@ extern "C" int sc_destroy(sc_handle h) {
 }
 
 extern "C" const char *sc_last_error(sc_handle h) { return h ? h->err : "null handle"; }
-extern "C" int sc_contact_stats(sc_handle h, int64_t *out2, int reset) {
-    if (!h || !out2) return SC_EINVAL;
+extern "C" int sc_contact_stats(sc_handle h, int64_t *out3, int reset) {
+    if (!h || !out3) return SC_EINVAL;
     SC_ON_DEVICE(h);
-    unsigned long long v[2];
+    unsigned long long v[3];
     SC_CUDA(h, cudaMemcpy(v, h->d_stats, sizeof v, cudaMemcpyDeviceToHost));      // synchronises: a diagnostic, not a hot-path call
-    out2[0] = (int64_t)v[0]; out2[1] = (int64_t)v[1];
+    out3[0] = (int64_t)v[0]; out3[1] = (int64_t)v[1]; out3[2] = (int64_t)v[2];
     if (reset) SC_CUDA(h, cudaMemset(h->d_stats, 0, sizeof v));
     return SC_OK;
 }
@@ -566,7 +566,8 @@ static int sc_features(sc_context *h, const float *states, int n, cudaStream_t s
 
 extern "C" int sc_window(sc_handle h, const float *parents, const float *parent_cache, int E, const int32_t *parent_idx,
                          int children, const float *actions, const float *targets, int nseq, const int32_t *sample_seq, int S,
-                         int nsteps, float *out_state, float *out_cost, float *out_info, float *out_cache, void *stream) {
+                         int nsteps, float *out_state, float *out_cost, float *out_info, float *out_cache, int32_t *out_overflow,
+                         void *stream) {
     if (!h) return SC_EINVAL;
     if (!parents || !actions || !targets || S < 1 || E < 1 || nseq < 1 || nsteps < 0)
         return sc_fail(h, SC_EINVAL, "sc_window: bad arguments (S=%d E=%d nseq=%d nsteps=%d)", S, E, nseq, nsteps);
@@ -578,7 +579,7 @@ extern "C" int sc_window(sc_handle h, const float *parents, const float *parent_
     int rc = sc_features(h, targets, nseq, st);
     if (rc) return rc;
     RolloutArgs a = {};
-    a.parent_cache = parent_cache; a.out_cache = out_cache; a.stats = h->d_stats;
+    a.parent_cache = parent_cache; a.out_cache = out_cache; a.out_overflow = out_overflow; a.stats = h->d_stats;
     a.parents = parents; a.parent_idx = parent_idx; a.children = children > 0 ? children : 1; a.actions = actions;
     a.targets = targets; a.tfeat = h->d_tfeat; a.sample_seq = sample_seq; a.S = S; a.nsteps = nsteps;
     a.out_state = out_state; a.out_cost = out_cost; a.out_info = out_info;

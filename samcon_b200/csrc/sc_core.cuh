@@ -691,7 +691,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
                 const float z = F(O_PW + 3 * b + 2) + F(O_RW + 9 * b + 6) * pt[0] + F(O_RW + 9 * b + 7) * pt[1] +
                                 F(O_RW + 9 * b + 8) * pt[2] - pt[3];
                 F(O_ZC + ST.npair + c) = z;
-                hits += z < T.cthresh ? 1 : 0;
+                hits += (z < T.cthresh ? 1 : 0) + (z <= 0.0f ? 1 << 16 : 0);      // inside the margin | touching
             }
         }
         F(O_CNT + slot) = i2f(hits);
@@ -734,7 +734,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
             float dist;
             if (pair_contact(S, ST, pr, pa, pb, n, dist)) {
                 F(O_ZC + pr) = dist;
-                hits += dist < T.cthresh ? 1 : 0;
+                hits += (dist < T.cthresh ? 1 : 0) + (dist <= 0.0f ? 1 << 16 : 0);
             }
         }
         F(O_CNT + LPS + slot) = i2f(hits);
@@ -742,13 +742,15 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
     SC_SYNC();
     SC_STAGE {
         SC_LANE;
-        int ofs = 0, ofs2 = 0, total = 0;        // ofs: this lane's first ground slot, ofs2: its first pair slot
+        int ofs = 0, ofs2 = 0, total = 0, touching = 0;   // ofs: this lane's first ground slot, ofs2: its first pair slot
 #pragma unroll
         for (int l = 0; l < LPS; l++) {
-            const int n = f2i(F(O_CNT + l)), n2 = f2i(F(O_CNT + LPS + l));
+            const int v = f2i(F(O_CNT + l)), v2 = f2i(F(O_CNT + LPS + l));
+            const int n = v & 0xffff, n2 = v2 & 0xffff;
             ofs += (l < slot ? n : 0) + n2;
             ofs2 += l < slot ? n2 : 0;
             total += n + n2;
+            touching += (v >> 16) + (v2 >> 16);
         }
 #if defined(SC_PROFILE) && defined(__CUDACC__)
         if (total > T.maxc) sc_prof_acc[23]++;
@@ -756,7 +758,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
 #endif
         const bool list = total > T.maxc && total <= HL_MAX;   // too many: compact (z, u) first, pick in parallel below
         if (total <= T.maxc || list) {
-            if (f2i(F(O_CNT + LPS + slot)) > 0)
+            if ((f2i(F(O_CNT + LPS + slot)) & 0xffff) > 0)
                 for (int i = 0; i < ST.pairs_per_lane; i++) {
                     const int pr = slot * ST.pairs_per_lane + i;
                     if (pr < ST.npair) {
@@ -767,7 +769,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
                         }
                     }
                 }
-            if (f2i(F(O_CNT + slot)) > 0)
+            if ((f2i(F(O_CNT + slot)) & 0xffff) > 0)
                 for (int i = 0; i < T.cand_per_lane; i++) {
                     const int c = slot * T.cand_per_lane + i;
                     if (c < T.ncand) {
@@ -781,7 +783,9 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
         }
         if (slot == 0) {
             F(O_NC) = i2f(total);
-            if (total > T.maxc) F(O_OVF) = i2f(f2i(F(O_OVF)) + 1);
+            // over the cap: the candidates dropped are the farthest ones -- speculative points that do not touch yet, unless
+            // more than maxc points touch (counted separately, in the upper half)
+            if (total > T.maxc) F(O_OVF) = i2f(f2i(F(O_OVF)) + 1 + (touching > T.maxc ? 1 << 16 : 0));
         }
     }
     SC_SYNC();
@@ -981,13 +985,19 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
     for (int m = 0; m < RPL; m++) {
         const int row = gs_row(RPL * slot + m, NCT);
         const bool live = row < nr;
+        // element (row, c) of the packed lower triangle: in the row's own run for c <= row, else in row c at a compile-time
+        // offset.  One address select and one unconditional load per element -- entries beyond the live system are whatever
+        // the scratch block holds and are replaced by zeros, never used (r1 computed max / min / triangular index per element
+        // behind a branch: 660 instructions and 35 branches before the first sweep, half of the Gauss-Seidel phase's time)
+        const float *rowp = S + (O_AM + row * (row + 1) / 2) * TILE, *colp = S + (O_AM + row) * TILE;
 #pragma unroll
         for (int c = 0; c < NRT; c++) {
-            const int hi = row > c ? row : c, lo = row > c ? c : row;
-            a[m][c] = (live && c < nr) ? F(O_AM + hi * (hi + 1) / 2 + lo) : 0.0f;
+            const float *p = row >= c ? rowp + c * TILE : colp + (c * (c + 1) / 2) * TILE;
+            const float v = *p;
+            a[m][c] = (live && c < nr) ? v : 0.0f;
         }
         res[m] = live ? F(O_RHS + row) : 0.0f;
-        dgi[m] = live ? 1.0f / F(O_AM + row * (row + 1) / 2 + row) : 0.0f;
+        dgi[m] = live ? 1.0f / rowp[row * TILE] : 0.0f;
     }
     // warm start: the normal rows begin at the cached impulses (contact_cache), friction rows at zero
 #pragma unroll
@@ -1409,7 +1419,10 @@ struct RolloutArgs {
     float *out_feat;           // [S,18] or null (feature-only mode)
     float *out_cost6;          // [S,6] total + 5 terms, or null (sc_cost)
     float *out_cache;          // [S,SC_CACHE_DIM] or null
-    unsigned long long *stats; // [2] or null: sample-sub-steps with more candidate hits than max_contacts, sample-sub-steps
+    int *out_overflow;         // [S] or null: sub-steps of the window in which the sample had more than max_contacts candidate
+                               // points inside the margin (low 16 bits) / touching, distance <= 0 (high 16 bits)
+    unsigned long long *stats; // [3] or null: sample-sub-steps with more candidates in the margin than max_contacts, sample-sub-steps
+                               // simulated, sample-sub-steps with more TOUCHING candidates than max_contacts
     long long *prof;           // developer builds (-DSC_PROFILE): per-phase cycle counters, else null
 };
 
@@ -1487,10 +1500,12 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
                 float *dst = a.out_cache + (size_t)k * SC_CACHE_DIM;
                 for (int j = slot; j < MAXC; j += LPS) { dst[j] = (float)f2i(F(O_PCU + j)); dst[MAXC + j] = F(O_PLAM + j); }
             }
+            if (a.out_overflow && slot == 0) a.out_overflow[k] = f2i(F(O_OVF));
 #if defined(__CUDACC__)
             if (a.stats && slot == 0 && a.nsteps > 0) {
-                atomicAdd(a.stats, (unsigned long long)f2i(F(O_OVF)));
+                atomicAdd(a.stats, (unsigned long long)(f2i(F(O_OVF)) & 0xffff));
                 atomicAdd(a.stats + 1, (unsigned long long)a.nsteps * T.nsub);
+                atomicAdd(a.stats + 2, (unsigned long long)(f2i(F(O_OVF)) >> 16));
             }
 #endif
             if (slot == 0 && (a.out_cost || a.out_cost6)) {

@@ -88,11 +88,11 @@ class GpuSamplePool:
 
     # ------------------------------------------------------------------ device-level API (C ABI 1:1)
     def contact_stats(self, reset=True):
-        """(sample-sub-steps whose candidate contacts exceeded max_contacts, sample-sub-steps simulated) since the last
-        reset.  Synchronises the device."""
-        out = (C.c_int64 * 2)()
+        """(sample-sub-steps with more candidate points inside the contact margin than max_contacts, sample-sub-steps
+        simulated, sample-sub-steps with more TOUCHING points than max_contacts) since the last reset.  Synchronises."""
+        out = (C.c_int64 * 3)()
         self._check(self._lib.sc_contact_stats(self._h, out, int(bool(reset))), "sc_contact_stats")
-        return int(out[0]), int(out[1])
+        return int(out[0]), int(out[1]), int(out[2])
 
     def empty_cache(self, n):
         """n contact-cache rows without contacts (ids -1, impulses 0)."""
@@ -101,10 +101,11 @@ class GpuSamplePool:
         return c
 
     def window(self, parents, actions, targets, nsteps, children=None, parent_idx=None, sample_seq=None, out=None,
-               parent_cache=None, out_cache=None):
+               parent_cache=None, out_cache=None, out_overflow=None):
         """One SamCon window for all samples.  Returns (state [S,132], cost [S], info [S,5]) on the device.
         ``parent_cache`` [E,CACHE_DIM]: the parents' contact caches (None: empty); ``out_cache`` [S,CACHE_DIM] receives
-        every sample's cache at the end of the window (pass True to have it allocated; it is then a 4th return value)."""
+        every sample's cache at the end of the window (pass True to have it allocated; it is then a 4th return value);
+        ``out_overflow`` int32 [S]: per sample, the sub-steps in which its candidate contacts exceeded max_contacts."""
         parents = self._f32(parents)
         actions = self._f32(actions)
         targets = self._f32(targets).reshape(-1, STATE_DIM)
@@ -134,7 +135,7 @@ class GpuSamplePool:
             raise ValueError("out_cache must be a contiguous float32 [S, CACHE_DIM] tensor on the pool's device")
         rc = self._lib.sc_window(self._h, _ptr(parents), _ptr(parent_cache), E, _ptr(parent_idx), int(children), _ptr(actions),
                                  _ptr(targets), nseq, _ptr(sample_seq), S, int(nsteps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
-                                 _ptr(out_cache), self._stream())
+                                 _ptr(out_cache), _ptr(out_overflow), self._stream())
         self._check(rc, "sc_window")
         return (*out, out_cache) if want_cache else out
 
@@ -247,8 +248,11 @@ class GpuSamplePool:
             raise RuntimeError("init() must be called before sim()")
         if not isinstance(actions, torch.Tensor):
             actions = np.asarray(actions, dtype=np.float32)
+        S = len(actions)
+        if getattr(self, "_ovf", None) is None or self._ovf.shape[0] != S:
+            self._ovf = torch.empty((S,), dtype=torch.int32, device=self.device)
         st, cost, info, cache = self.window(self._elites, actions, np.asarray(target_state, dtype=np.float32), nsteps,
-                                            parent_cache=self._elite_cache, out_cache=True)
+                                            parent_cache=self._elite_cache, out_cache=True, out_overflow=self._ovf)
         self._last = (st, cost, info, cache)
         # device -> pinned host staging (allocated once per sample count), one synchronisation for the three results;
         # the widening to the reference's float64 happens on the device (a numpy astype of 1.4 M values costs more
@@ -272,6 +276,7 @@ class GpuSamplePool:
         idx = self._i32(np.asarray(elite_inds, dtype=np.int32))
         self._elites = self.gather_rows(self._last[0], idx)
         self._elite_cache = self.gather_rows(self._last[3], idx)      # the snapshot carries the contact cache
+        self.elite_overflow = self._ovf[idx.long()]                   # per kept sample: sub-steps over the contact cap
 
     def close(self):
         if not self._closed and self._h:

@@ -78,6 +78,6 @@ def test_sc_create_validates_the_model_before_touching_cuda(lib_path, character)
     lib.sc_destroy(h)
     assert lib.sc_create(None, C.byref(m), 0) == -1
     assert lib.sc_destroy(None) == -1 and lib.sc_launch_count(None) == 0
-    assert lib.sc_window(None, None, None, 1, None, 1, None, None, 1, None, 1, 1, None, None, None, None, None) == -1
+    assert lib.sc_window(None, None, None, 1, None, 1, None, None, 1, None, 1, 1, None, None, None, None, None, None) == -1
     assert lib.sc_select(None, None, None, 1, 1, None, None, 0, None) == -1
     assert lib.sc_last_error(None) == b"null handle"

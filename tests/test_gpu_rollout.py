@@ -212,21 +212,21 @@ def test_contact_cache_travels_with_the_state(pool, oracle):
 
 
 def test_contact_cap_statistics(pool):
-    """sc_contact_stats: how often more candidate points were inside the margin than max_contacts.  A humanoid lying on
-    the ground overflows in every sub-step, an airborne one never."""
+    """sc_contact_stats: how often more candidate points were inside the margin than max_contacts, and how often more
+    than that were actually touching.  A humanoid lying on the ground overflows in every sub-step, an airborne one never."""
     rng = np.random.default_rng(22)
     pool.contact_stats(reset=True)
     air = np.array([rand_state(rng, 0.3, 3.0) for _ in range(5)]).astype(np.float32)
     pool.window(air, air[:, 7:75].copy(), air[0], 10, children=1)
-    ov, n = pool.contact_stats()
-    assert (ov, n) == (0, 5 * 10 * 2)
+    ov, n, hard = pool.contact_stats()
+    assert (ov, n, hard) == (0, 5 * 10 * 2, 0)
     lying = stand(rng, 0.02, 0.0, 0.08)
     lying[3:7] = [0, 0, 0, 1]
     lying = np.repeat(lying[None], 3, axis=0).astype(np.float32)
     pool.window(lying, lying[:, 7:75].copy(), lying[0], 10, children=1)
-    ov, n = pool.contact_stats()
-    assert n == 3 * 10 * 2 and ov >= n // 2
-    assert pool.contact_stats() == (0, 0)
+    ov, n, hard = pool.contact_stats()
+    assert n == 3 * 10 * 2 and ov >= n // 2 and 0 < hard <= ov
+    assert pool.contact_stats() == (0, 0, 0)
 
 
 def test_entry_points_restore_the_callers_device(character):

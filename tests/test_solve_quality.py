@@ -92,10 +92,29 @@ def test_gpu_walk_solve_tracks_motion(walk_cfg, character, nSample, nSave):
     cfg.motion_seq = name
     pool = GpuSamplePool(character, 0)
     algo = SamCon(cfg, ld, 1, 30, nSample, nSave, pool=pool)
+    kept_overflow = []
+    keep = pool.keep
+
+    def keep_and_count(inds):             # per window: how often the samples that were KEPT ran into the contact cap
+        keep(inds)
+        ov = pool.elite_overflow
+        kept_overflow.append(((ov & 0xffff).float().mean().item() / 200.0, (ov >> 16).float().mean().item() / 200.0))
+    pool.keep = keep_and_count
+    pool.contact_stats(reset=True)
     try:
         res, info = algo.sample(save=False)
+        ov_all, n_all, hard_all = pool.contact_stats()
     finally:
         algo.close()
+    # The 8-contact cap.  More than 8 candidate points inside the 2 cm margin is common (two flat feet are 8 already, an arm
+    # hanging next to the torso adds speculative link-link points), but what the cap drops first are the farthest, not yet
+    # touching ones.  More than 8 TOUCHING points -- a live contact dropped -- happens to samples that are falling over
+    # anyway and (almost) never to the ones the search keeps.
+    ko = np.array(kept_overflow)
+    print(f"contact cap: {ov_all / n_all:.2%} of all sample-sub-steps had more than 8 candidates in the margin ({ko[:, 0].mean():.2%} "
+          f"of the elites'), {hard_all / n_all:.3%} more than 8 touching ({ko[:, 1].mean():.4%} of the elites', worst window "
+          f"{ko[:, 1].max():.4%})")
+    assert ko[:, 1].mean() < 0.002
     best = res[name]["path_0"]
     dz = np.abs(best["simulated_state"][:, 2] - best["target_state"][:, 2])
     elite_best = np.array([info["total_cost"][t][info["elite_inds"][t][0]] for t in range(30)])

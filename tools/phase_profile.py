@@ -18,7 +18,9 @@ from helpers import stand, near_action, rand_state
 NAMES = ["load", "fk", "pd_term", "aba_pd", "collide", "aba", "fk_vel", "c_rhs", "c_assembly", "c_gs", "c_apply", "integrate",
          "features+cost+store", "cta_barrier_wait", "-", "idle/other"]
 from samcon_b200.model import SimParams
-cfg = Config("walk"); ch = Character.from_config(cfg, SimParams(self_collision=os.environ.get("SC_SELF", "1") == "1")); pool = GpuSamplePool(ch, 0)
+cfg = Config("walk")
+ch = Character.from_config(cfg, SimParams(self_collision=os.environ.get("SC_SELF", "1") == "1", num_solver_iters=int(os.environ.get("SC_NITER", "10"))))
+pool = GpuSamplePool(ch, 0)
 pool._lib.sc_prof_read.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
 rng = np.random.default_rng(0)
 args = sys.argv[1:]
@@ -34,7 +36,7 @@ def report(tag, ms):
     tot = ph.sum() + v[26:31].sum()
     print(f"== {tag}: {ms:.2f} ms")
     for n, x in zip(NAMES, ph):
-        if x: print(f"  {n:22s} {100*x/tot:6.2f}%")
+        if x: print(f"  {n:22s} {100*x/tot:6.2f}%  {ms*x/tot:7.3f} ms")
     for n, i in (("wait before collide (after aba)", 30), ("wait after collide", 26), ("wait after assembly", 27), ("wait after gs", 28), ("wait after apply", 29)):
         if v[i]: print(f"  {n:32s} {100*v[i]/tot:6.2f}%")
     if st[0]:
@@ -53,14 +55,14 @@ for mode in modes:
         _, _, targets = bench.workload_inputs(9)
         d_targets = torch.tensor(targets, dtype=torch.float32, device="cuda")
         limits = torch.tensor(cfg.values, dtype=torch.float32, device="cuda")
-        parents = d_targets[0:1].repeat(E, 1).contiguous()
+        parents, pcache = d_targets[0:1].repeat(E, 1).contiguous(), None
         for w in range(1, 9):
             act = pool.sample_gen(d_targets[w], limits, S, seed=cfg.seed, window=w)
             pool._lib.sc_prof_read(pool._h, buf)
-            e0.record(); st, cost, info = pool.window(parents, act, d_targets[w], 100); e1.record(); torch.cuda.synchronize()
+            e0.record(); st, cost, info, cache = pool.window(parents, act, d_targets[w], 100, parent_cache=pcache, out_cache=True); e1.record(); torch.cuda.synchronize()
             report(f"walk window {w} S={S}", e0.elapsed_time(e1))
             idx, ec = pool.select(cost, E)
-            parents = pool.gather_rows(st, idx.reshape(-1))
+            parents, pcache = pool.gather_rows(st, idx.reshape(-1)), pool.gather_rows(cache, idx.reshape(-1))
             print(f"  elite cost best {ec[0,0].item():.3f} worst {ec[0,-1].item():.3f}; all-sample mean {cost.mean().item():.3f}")
         continue
     base = np.array([stand(rng, 0.03, 0.1, 0.985) if mode == "stand" else rand_state(rng, 0.3, 3.0) for _ in range(64)])

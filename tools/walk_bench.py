@@ -21,14 +21,14 @@ _, _, targets = bench.workload_inputs(W + 1)
 d_targets = torch.tensor(targets, dtype=torch.float32, device="cuda")
 limits = torch.tensor(cfg.values, dtype=torch.float32, device="cuda")
 E = S // 10
-parents = d_targets[0:1].repeat(E, 1).contiguous()
+parents, pcache = d_targets[0:1].repeat(E, 1).contiguous(), None
 ms = []
 for w in range(1, W + 1):
     act = pool.sample_gen(d_targets[w], limits, S, seed=cfg.seed, window=w)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); st, cost, info = pool.window(parents, act, d_targets[w], 100); e1.record(); torch.cuda.synchronize()
+    e0.record(); st, cost, info, cache = pool.window(parents, act, d_targets[w], 100, parent_cache=pcache, out_cache=True); e1.record(); torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
     idx, ec = pool.select(cost, E)
-    parents = pool.gather_rows(st, idx.reshape(-1))
+    parents, pcache = pool.gather_rows(st, idx.reshape(-1)), pool.gather_rows(cache, idx.reshape(-1))
 print(os.environ.get("SC_LIB", "default"), "self" if ch.sim.self_collision else "noself", f"S={S}",
       " ".join(f"{m:.1f}" for m in ms), f"| mean of last {W - 2}: {np.mean(ms[2:]):.2f} ms  best elite cost {ec[0, 0].item():.3f}")
