@@ -358,16 +358,24 @@ __global__ void sc_motion_states_kernel(const float *__restrict__ poses, const i
     const float *A = poses + (size_t)(f0 + frame) * pd, *B = poses + (size_t)(f0 + next) * pd;
     float *o = out + ((size_t)q * nt + it) * SC_STATE_DIM;
     const float *qa = A + 3 + 4 * r, *qb = B + 3 + 4 * r;
-    // getQuaternionSlerp: shortest arc; (anti)parallel inputs return the start orientation
-    const float mag = sqrtf((qa[0] * qa[0] + qa[1] * qa[1] + qa[2] * qa[2] + qa[3] * qa[3]) *
-                            (qb[0] * qb[0] + qb[1] * qb[1] + qb[2] * qb[2] + qb[3] * qb[3]));
-    const float prod = (qa[0] * qb[0] + qa[1] * qb[1] + qa[2] * qb[2] + qa[3] * qb[3]) / mag;
-    float s0 = 1.0f, s1 = 0.0f;
-    if (fabsf(prod) < 1.0f - 1.1920929e-7f) {
-        const float theta = acosf(fabsf(prod)), d = sinf(theta), sign = prod < 0 ? -1.0f : 1.0f;
-        s0 = sinf((1.0f - frac) * theta) / d;
-        s1 = sinf(sign * frac * theta) / d;
+    // getQuaternionSlerp: shortest arc, weights sin((1-f) theta) / sin(theta) and +-sin(f theta) / sin(theta) with theta the
+    // angle between the two 4-vectors; (anti)parallel inputs return the start orientation.  The reference takes theta from
+    // acos(|<q0,q1>|) in double; in float that loses everything below 7e-4 rad (consecutive frames!), so theta comes from the
+    // chord |+-q1 - q0| = 2 sin(theta / 2) instead, and the weights go over into their limit 1 - f, +-f for tiny angles.
+    const float na = rsqrtf(qa[0] * qa[0] + qa[1] * qa[1] + qa[2] * qa[2] + qa[3] * qa[3]);
+    const float nb = rsqrtf(qb[0] * qb[0] + qb[1] * qb[1] + qb[2] * qb[2] + qb[3] * qb[3]);
+    const float prod = (qa[0] * qb[0] + qa[1] * qb[1] + qa[2] * qb[2] + qa[3] * qb[3]) * na * nb;
+    const float sign = prod < 0 ? -1.0f : 1.0f;
+    float ch2 = 0.0f;
+    for (int c = 0; c < 4; c++) { const float d = sign * qb[c] * nb - qa[c] * na; ch2 += d * d; }
+    const float theta = 2.0f * asinf(fminf(1.0f, 0.5f * sqrtf(ch2)));
+    float s0 = 1.0f - frac, s1 = sign * frac;
+    if (theta > 1e-3f) {
+        const float d = 1.0f / sinf(theta);
+        s0 = sinf((1.0f - frac) * theta) * d;
+        s1 = sign * sinf(frac * theta) * d;
     }
+    if (ch2 == 0.0f) { s0 = 1.0f; s1 = 0.0f; }
     float *oq = o + 3 + 4 * r;
     for (int c = 0; c < 4; c++) oq[c] = qa[c] * s0 + qb[c] * s1;
     // angular velocity: axis-angle of q1 (x) conj(q0) (root, world frame) or conj(q0) (x) q1 (joints, local frame), over the

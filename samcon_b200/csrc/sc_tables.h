@@ -83,7 +83,7 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
         for (int p = 0; p < m->nprim; p++) {
             if (m->prim_body[p] < 0 || m->prim_body[p] >= m->nb) SC_FAIL("bad prim_body");
             ST->prim_body[p] = (unsigned char)m->prim_body[p];
-            const float *q = m->prim + 7 * p;
+            const auto *q = m->prim + 7 * p;      // (auto: tests/emu/emu64.cpp compiles this file with float := double)
             for (int k = 0; k < 7; k++) ST->prim[8 * p + k] = q[k];
             const double dx = q[3] - q[0], dy = q[4] - q[1], dz = q[5] - q[2];
             ST->prim[8 * p + 7] = (float)(q[6] + 0.5 * sqrt(dx * dx + dy * dy + dz * dz));

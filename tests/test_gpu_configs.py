@@ -37,9 +37,11 @@ def test_cartwheel_window_parity(oracle):
             rms = joint_rms(st.cpu().numpy(), ost)
             crel = np.abs(cost.cpu().numpy() - ocost) / np.abs(ocost)
             print(f"cartwheel t0={t0}: joint rms median {np.median(rms):.2e} max {rms.max():.2e}; cost rel max {crel.max():.2e}")
-            # hand-stand phases are contact-rich and occasionally chaotic: the bar is on the distribution
-            assert np.median(rms) < 1e-4 and (rms < 1e-3).mean() >= 0.75 and rms.max() < 0.1
-            assert np.median(crel) < 1e-4 and (crel < 1e-3).mean() >= 0.75
+            # hand-stand phases are contact-rich and occasionally chaotic (tests/test_f64_kernel_build.py): the bar is on the
+            # distribution
+            frac = 0.75 if t0 == 0.9 else 0.95         # hands striking the ground at t0 = 0.9: the chaotic phase
+            assert np.median(rms) < 1e-4 and (rms < 1e-3).mean() >= frac and rms.max() < 0.1
+            assert np.median(crel) < 1e-4 and (crel < 1e-3).mean() >= frac
             links = {int(r[0]) for s in ost for r in o.contacts_full(s) if r[1] < 0}
             checked += len(links & {14, 15, 16, 18, 19, 20, 12, 13, 17})          # arm / hand links touched the ground
         assert checked > 0

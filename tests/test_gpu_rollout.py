@@ -5,8 +5,9 @@ after one window; elite index sets equal whenever costs are separated by more th
 
 Contact-rich samples with the cfg's large hip noise (0.8 rad) are occasionally *chaotic*: rounding-level
 differences grow ~50x per simulated millisecond while feet chatter on the ground.  The float64 build of the very
-same kernel source deviates from the oracle on exactly those samples, so for the cfg-noise window
-the bar is applied to the distribution: >= 95 % of the samples inside the tolerance, tight median, bounded worst case.
+same kernel source deviates from the oracle on exactly those samples (tests/test_f64_kernel_build.py shows it on this
+window), so for the cfg-noise window the bar is applied to the distribution: >= 98 % of the samples inside the
+tolerance, tight median, bounded worst case.
 """
 import numpy as np
 import pytest
@@ -79,8 +80,8 @@ def test_walk_window_and_elites(pool, oracle):
     crel = np.abs(cost - ocost) / np.abs(ocost)
     print(f"joint rms: median {np.median(rms):.2e} p95 {np.quantile(rms, .95):.2e} max {rms.max():.2e}; "
           f"cost rel: median {np.median(crel):.2e} max {crel.max():.2e}")
-    assert np.median(rms) < 5e-5 and (rms < JOINT_TOL).mean() >= 0.95 and rms.max() < 0.05
-    assert np.median(crel) < 1e-4 and (crel < COST_RTOL).mean() >= 0.95
+    assert np.median(rms) < 5e-5 and (rms < JOINT_TOL).mean() >= 0.98 and rms.max() < 0.05
+    assert np.median(crel) < 1e-4 and (crel < COST_RTOL).mean() >= 0.98
     idx, ec = pool.select(cost, E)
     gi = idx.cpu().numpy()[0]
     oi = oracle.topk(ocost, E)
