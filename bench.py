@@ -282,9 +282,13 @@ def run_ours(args):
             dist.all_gather_into_tensor(all_st, st.contiguous())
             all_ch = torch.empty((world * S, cache.shape[1]), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(all_ch, cache.contiguous())
-            ref = torch.argsort(all_cost, stable=True)[:E * world]
-            ok = torch.equal(ref, ids) and torch.equal(all_st[ref[rank * E:(rank + 1) * E]], parents) \
-                and torch.equal(all_ch[ref[rank * E:(rank + 1) * E]], pcache)
+            # (all_gathered rows are in (rank, local) order; ids are in the unsharded search's numbering)
+            lr = torch.arange(world * S, device=dev)
+            order = search.global_sample_ids(lr // S, lr % S)
+            ref_pos = torch.argsort(all_cost, stable=True)[:E * world]
+            # ties between ranks aside (measure zero), the E cheapest samples, cheapest first
+            ok = torch.equal(order[ref_pos], ids) and torch.equal(all_st[ref_pos[rank::world]], parents) \
+                and torch.equal(all_ch[ref_pos[rank::world]], pcache)
             flag = torch.tensor([1 if ok else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             check = "ok" if flag.item() == 1 else "MISMATCH"

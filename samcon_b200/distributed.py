@@ -1,15 +1,19 @@
 """Samples of one SamCon window sharded over the GPUs of one box (one process per GPU).
 
 The reference shards the nSave elites contiguously over ``num_processes`` workers and gathers pickled result
-lists over pipes (/root/reference/samcon/core/samcon.py:85-90, 168-176).  Here rank r owns samples
-[r*S_loc, (r+1)*S_loc) and therefore -- sample k descends from elite k // children (samcon.py:31-35) -- the
-contiguous elite block [r*E_loc, (r+1)*E_loc).  Rollouts need no communication.  The one exchange step per
-window is elite selection:
+lists over pipes (/root/reference/samcon/core/samcon.py:85-90, 168-176).  Here the elites -- which come out of the
+selection in ascending cost order -- are dealt to the ranks ROUND ROBIN: rank r simulates the children of elites
+r, r + N, r + 2N, ...  (Contiguous blocks, round 1's choice, hand rank 0 the cheapest elites and rank N-1 the costliest,
+and costly parents are the ones with many contacts: on 4 GPUs the last rank's rollouts were 0.9 ms per window slower
+than the first's and every window waits for the slowest rank.)  Local sample j of rank r is sample
+((j // children) * N + r) * children + j % children of the unsharded search (sample k descends from elite k // children,
+samcon.py:31-35), so a sharded search fed the same actions is the unsharded one.  Rollouts need no communication.  The
+one exchange step per window is elite selection:
 
   1. every rank takes its local top-min(E, S_loc) (cost, index) with the segmented radix top-k kernel,
-  2. NCCL all_gather of those (cost f32, index i32) lists  (8 B x E per rank),
+  2. ONE NCCL all_gather of those lists, cost f32 and index i32 side by side  (8 B x E per rank),
   3. every rank runs the identical final top-E over the N*E candidates (ties: lower global sample index),
-  4. rank r fetches the snapshots (132-float state + contact cache) of ITS parent block -- E_loc rows, wherever they
+  4. rank r fetches the snapshots (132-float state + contact cache) of ITS parents -- E_loc rows, wherever they
      were simulated -- straight out of the owners' result buffers over NVLink: the buffers live in symmetric memory
      (torch.distributed._symmetric_memory, CUDA VMM handles exchanged once at start-up) and one gather kernel
      (sc_gather_rows_peer) reads peer HBM through NVSwitch.  No collective, no padding, no host synchronisation:
@@ -44,6 +48,7 @@ class ShardedSearch:
             raise ValueError("nSave must split evenly over ranks and nSample over elites")
         self.pool, self.S_loc, self.E, self.rank, self.world, self.group = pool, S_local, E_global, rank, world, group
         self.E_loc = E_global // world
+        self.children = S_local // self.E_loc
         self.Ec = min(E_global, S_local)          # candidates a rank can contribute
         self.exchange = "local" if world == 1 else None
         self._win = 0
@@ -86,6 +91,14 @@ class ShardedSearch:
         ns = self.S_loc * STATE_DIM
         return b[:ns].view(self.S_loc, STATE_DIM), b[ns:].view(self.S_loc, CACHE_DIM)
 
+    def global_sample_ids(self, rank, local):
+        """Index in the unsharded search of local sample `local` of rank `rank` (tensors or ints)."""
+        return ((local // self.children) * self.world + rank) * self.children + local % self.children
+
+    def my_slots(self):
+        """Positions in the global (ascending-cost) elite list of the parents this rank simulates."""
+        return slice(self.rank, self.E, self.world)
+
     # ------------------------------------------------------------------ the exchange
     def select_global(self, cost):
         """Local top-Ec, all_gather of (cost, index), identical final top-E on every rank.
@@ -95,41 +108,45 @@ class ShardedSearch:
         lidx, lcost = lidx.reshape(-1), lcost.reshape(-1)
         if self.world == 1:
             return torch.zeros(self.E, dtype=torch.int32, device=dev), lidx[:self.E].contiguous(), lcost[:self.E], lidx[:self.E].to(torch.int64)
-        # flat [world * Ec] outputs: the layout both NCCL and gloo accept for a 1-D input
-        all_cost = torch.empty((self.world * self.Ec,), dtype=torch.float32, device=dev)
-        all_idx = torch.empty((self.world * self.Ec,), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(all_cost, lcost.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_idx, lidx.contiguous(), group=self.group)
+        # one collective: costs and (bit-cast) indices side by side; flat output, the layout both NCCL and gloo accept
+        mine = torch.cat([lcost, lidx.view(torch.float32)]).contiguous()
+        both = torch.empty((self.world * 2 * self.Ec,), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(both, mine, group=self.group)
+        both = both.view(self.world, 2, self.Ec)
+        all_cost = both[:, 0, :].contiguous().view(-1)
+        all_idx = both[:, 1, :].contiguous().view(torch.int32).view(-1)
         pos, gcost = self.pool.select(all_cost, self.E)
         pos = pos.reshape(-1).to(torch.int64)
         win_rank = (pos // self.Ec).to(torch.int32)
         win_local = all_idx[pos].contiguous()
-        return win_rank, win_local, gcost.reshape(-1), win_rank.to(torch.int64) * self.S_loc + win_local.to(torch.int64)
+        return win_rank, win_local, gcost.reshape(-1), self.global_sample_ids(win_rank.to(torch.int64), win_local.to(torch.int64))
 
     def fetch_block(self, win_rank, win_local, st, cache):
-        """Snapshots of this rank's parent block: (states [E_loc,132], caches [E_loc,CACHE_DIM])."""
-        lo, hi = self.rank * self.E_loc, (self.rank + 1) * self.E_loc
+        """Snapshots of this rank's parents (elites rank, rank + N, ...): (states [E_loc,132], caches [E_loc,CACHE_DIM])."""
+        sl = self.my_slots()
         if self.world == 1:
-            return self.pool.gather_rows(st, win_local[lo:hi]), self.pool.gather_rows(cache, win_local[lo:hi])
+            return self.pool.gather_rows(st, win_local[sl]), self.pool.gather_rows(cache, win_local[sl])
         if self.exchange == "nvlink-p2p":
             p = self._win & 1
-            r, l = win_rank[lo:hi].contiguous(), win_local[lo:hi].contiguous()
+            r, l = win_rank[sl].contiguous(), win_local[sl].contiguous()
             return (self.pool.gather_rows_peer(self._peer_state[p], r, l, STATE_DIM),
                     self.pool.gather_rows_peer(self._peer_cache[p], r, l, CACHE_DIM))
-        # collective fall-back: block d of the send buffer = the rows of rank d's parent block that live here
+        # collective fall-back: block d of the send buffer = the rows of rank d's parents that live here
         dev = st.device
         mine = win_rank == self.rank
         safe = torch.where(mine, win_local, torch.zeros_like(win_local)).to(torch.int32)
         rows = torch.cat([self.pool.gather_rows(st, safe), self.pool.gather_rows(cache, safe)], dim=1)      # [E, ROW]
-        send = torch.where(mine[:, None], rows, torch.zeros((), dtype=torch.float32, device=dev)).contiguous()
+        rows = torch.where(mine[:, None], rows, torch.zeros((), dtype=torch.float32, device=dev))
+        send = rows.view(self.E_loc, self.world, ROW).transpose(0, 1).contiguous()         # [d, j] = elite j * N + d
         recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send, group=self.group)                  # recv[s*E_loc + j] = rank s's copy of my row j
-        blk = recv.view(self.world, self.E_loc, ROW).sum(dim=0)
+        dist.all_to_all_single(recv.view(-1, ROW), send.view(-1, ROW), group=self.group)    # recv[s, j] = rank s's copy of my parent j
+        blk = recv.sum(dim=0)
         return blk[:, :STATE_DIM].contiguous(), blk[:, STATE_DIM:].contiguous()
 
     def select_and_exchange(self, st, cost, cache=None):
-        """(st [S_loc,132], cost [S_loc], cache [S_loc,CACHE_DIM]) of this rank -> (parent block states [E_loc,132], parent
-        block caches, elite global sample ids [E], elite costs [E]); ids and costs identical on every rank."""
+        """(st [S_loc,132], cost [S_loc], cache [S_loc,CACHE_DIM]) of this rank -> (this rank's next parents [E_loc,132],
+        their caches, elite sample ids in the unsharded search's numbering [E], elite costs [E]); ids and costs identical
+        on every rank."""
         if cache is None:
             cache = torch.zeros((st.shape[0], CACHE_DIM), dtype=torch.float32, device=st.device)
             cache[:, :CACHE_DIM // 2] = -1.0

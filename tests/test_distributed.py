@@ -57,8 +57,10 @@ def _worker(rank, world, port, out):
         search = ShardedSearch(pool, S_loc, E, rank, world)
         assert search.exchange == "all_to_all"                   # no symmetric memory on CPU tensors: the collective path
         f = lambda x: torch.tensor(x, dtype=torch.float32)
-        acts = f(actions[rank * S_loc:(rank + 1) * S_loc])
-        blk, bcache, ids, ecost, _ = search.window(f(parents[rank * E_loc:(rank + 1) * E_loc]), acts, f(target), 15)
+        # elites are dealt round robin; local sample j is sample gid[j] of the unsharded search
+        gid = search.global_sample_ids(rank, torch.arange(S_loc)).numpy()
+        acts = f(actions[gid])
+        blk, bcache, ids, ecost, _ = search.window(f(parents[rank::world]), acts, f(target), 15)
         # second window from the exchanged parent block, contact caches included
         blk2, bcache2, ids2, ecost2, _ = search.window(blk, acts, f(target), 15, parent_cache=bcache)
         out[rank] = (blk.numpy(), bcache.numpy(), ids.numpy(), ecost.numpy(), blk2.numpy(), bcache2.numpy(), ids2.numpy(), ecost2.numpy())
@@ -87,12 +89,12 @@ def test_two_rank_search_equals_unsharded():
         blk, bcache, ids, ecost, blk2, bcache2, ids2, ecost2 = out[r]
         assert list(ids) == list(ref_ids)                        # global sample ids of the elites, ascending cost
         np.testing.assert_array_equal(ecost, ec[0].numpy())
-        np.testing.assert_array_equal(blk, ref_states[r * E_loc:(r + 1) * E_loc].numpy())      # x + 0 exchange is exact
-        np.testing.assert_array_equal(bcache, ref_cache[r * E_loc:(r + 1) * E_loc].numpy())
+        np.testing.assert_array_equal(blk, ref_states[r::world].numpy())                       # x + 0 exchange is exact
+        np.testing.assert_array_equal(bcache, ref_cache[r::world].numpy())
         assert list(ids2) == list(idx2[0].numpy())
         np.testing.assert_array_equal(ecost2, ec2[0].numpy())
-        np.testing.assert_array_equal(blk2, st2[idx2[0].long()][r * E_loc:(r + 1) * E_loc].numpy())
-        np.testing.assert_array_equal(bcache2, cache2[idx2[0].long()][r * E_loc:(r + 1) * E_loc].numpy())
+        np.testing.assert_array_equal(blk2, st2[idx2[0].long()][r::world].numpy())
+        np.testing.assert_array_equal(bcache2, cache2[idx2[0].long()][r::world].numpy())
 
 
 def _seq_worker(rank, world, port, out):
