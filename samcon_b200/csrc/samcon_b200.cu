@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *_
     {
         const int4 *src = reinterpret_cast<const int4 *>(gT);
         int4 *dst = reinterpret_cast<int4 *>(smem);
-        for (int i = threadIdx.x; i < TABLE_WORDS / 4; i += 32 * WPB) dst[i] = src[i];
+        for (int i = threadIdx.x; i < TABLE_WORDS / 4; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
     const Tables &T = *reinterpret_cast<const Tables *>(smem);
@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *_
     // (rollout_tile has CTA-wide phase barriers); a warp without a tile passes tile0 >= S.
     const int per = ntiles / gridDim.x, extra = ntiles % gridDim.x;
     const int mine = per + ((int)blockIdx.x < extra ? 1 : 0), first = blockIdx.x * per + min((int)blockIdx.x, extra);
-    const int rounds = (mine + WPB - 1) / WPB, wpr = rounds ? (mine + rounds - 1) / rounds : 0;
+    // WPB is the build's ceiling; the launch brings only as many warps as a round needs (blockDim.x / 32 = wpr of the fullest
+    // CTA, see sc_launch_rollout), so no warp sits at the phase barriers without a tile round after round
+    const int nw = blockDim.x >> 5;
+    const int rounds = (mine + nw - 1) / nw, wpr = rounds ? (mine + rounds - 1) / rounds : 0;
     for (int r = 0; r < rounds; r++) {
         const int t = r * wpr + warp;
         const bool active = warp < wpr && t < mine;
@@ -550,13 +553,19 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a, cudaStream_t s
     // all SMs even when there are few tiles (walk.yml's own nSample = 2000 is 500 tiles: 3-4 warps on each of 148 SMs
     // beat 10 warps on 50 of them); the kernel deals the tiles evenly
     const int grid = ntiles < h->grid_cap ? ntiles : h->grid_cap;
+    // warps per CTA: the fewest that keep the number of rounds the full CTA would need.  10 000 samples are 17 tiles on the
+    // fullest SM = 2 rounds either way, and 9 warps do them without a tenth warp idling at every phase barrier (27.5 vs
+    // 28.0 ms per window); walk.yml's own 2000 samples are 4 tiles per SM: 4 warps instead of 10.
+    const int mine = (ntiles + grid - 1) / grid, rounds = (mine + WPB - 1) / WPB;
+    const int nw = (mine + rounds - 1) / rounds, threads = 32 * nw;
+    const int smem = (TABLE_WORDS + nw * WORDS_PER_TILE) * 4;
 #if defined(SC_PROFILE)
     RolloutArgs ap = a;
     if (!h->d_prof) { cudaMalloc(&h->d_prof, SC_NPHASE * sizeof(long long)); cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long)); }
     ap.prof = a.nsteps > 0 ? h->d_prof : nullptr;
-    sc_rollout_kernel<WPB><<<grid, 32 * WPB, h->smem_bytes, st>>>(h->d_tables, ap);
+    sc_rollout_kernel<WPB><<<grid, threads, smem, st>>>(h->d_tables, ap);
 #else
-    sc_rollout_kernel<WPB><<<grid, 32 * WPB, h->smem_bytes, st>>>(h->d_tables, a);
+    sc_rollout_kernel<WPB><<<grid, threads, smem, st>>>(h->d_tables, a);
 #endif
     h->launches++;
     SC_CUDA(h, cudaGetLastError());
