@@ -8,12 +8,36 @@ import sys
 import numpy as np
 import pytest
 
-pybullet = pytest.importorskip("pybullet")
 REF = "/root/reference"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pybullet_windows.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(GOLDEN), reason="no reference goldens: tests/golden/make_pybullet_golden.py needs pybullet==3.2.5")
+def test_committed_pybullet_goldens():
+    """Oracle vs windows produced by the REFERENCE env under real PyBullet (tests/golden/make_pybullet_golden.py), at
+    BASELINE.json's tolerance.  The file cannot be produced in the build image; once somebody commits it this test is what
+    pins the oracle's physics (and lifts "parity unpinned")."""
+    from helpers import joint_rms
+    from oracle.oracle import Oracle
+    from samcon_b200.config import Config
+    from samcon_b200.model import Character
+    g = np.load(GOLDEN)
+    keys = sorted(k[:-6] for k in g.files if k.endswith("_state"))
+    assert keys
+    for key in keys:
+        cfgname = "cartwheel" if key == "cartwheel" else "walk"
+        o = Oracle(Character.from_config(Config(cfgname)))
+        parents, actions, target = g[f"{key}_parents"], g[f"{key}_actions"], g[f"{key}_target"]
+        for p, a, rs, rc in zip(parents, actions, g[f"{key}_state"], g[f"{key}_cost"]):
+            st, cost, _ = o.window(p[None], a[None], target, 100)
+            assert joint_rms(st, rs[None])[0] < 1e-3 and abs(cost[0] - rc) <= 1e-3 * abs(rc), key
+
+
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout absent")
 def test_one_window_against_real_pybullet(oracle, walk_cfg):
+    pytest.importorskip("pybullet")
     sys.path.insert(0, REF)
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
     from helpers import near_action, stand
