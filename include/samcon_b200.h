@@ -33,6 +33,7 @@ extern "C" {
 #define SC_CACHE_DIM (2 * SC_MAX_CONTACTS) /* contact-cache row: candidate ids (as floats, -1 = empty), normal impulses */
 #define SC_MAX_PRIMS 24   /* self-collision primitives (sphere-swept segments) */
 #define SC_MAX_PAIRS 128  /* self-collision primitive pairs */
+#define SC_MAX_BOXES 8    /* box primitives with an exact narrow phase */
 
 #define SC_OK 0
 #define SC_EINVAL (-1)
@@ -73,6 +74,11 @@ typedef struct sc_model {
     float friction_self;         /* link lateral friction x link lateral friction */
     float warmstart;             /* 0..1: factor on a persisting contact's cached normal impulse (0 = stateless contacts) */
     float spinning_friction, spinning_friction_self; /* must be 0: the torsional row exists in the CPU oracle only */
+    /* exact boxes in the link-vs-link narrow phase (feet, upper arms, forearms): nbox = 0 treats every box as its capsule
+     * stand-in `prim` describes */
+    int32_t nbox;
+    const int32_t *prim_box;     /* [nprim] box index of the primitive, -1 if it is a sphere / capsule */
+    const float *box;            /* [nbox,15] body frame: centre xyz, axes R (row major, v_body = R v_box), half extents */
 } sc_model;
 
 typedef struct sc_context *sc_handle;

@@ -53,7 +53,7 @@ class Oracle:
         sp = character.sim
         simp = [sp.dt, sp.num_substeps, sp.num_solver_iters, *sp.gravity, sp.friction, sp.erp,
                 sp.contact_threshold, sp.max_contacts, sp.max_velocity, float(bool(sp.self_collision)), sp.friction_self,
-                sp.warmstart, sp.spinning_friction, sp.spinning_friction_self]
+                sp.warmstart, sp.spinning_friction, sp.spinning_friction_self, float(bool(sp.exact_box_contacts))]
         self.cache_dim = 2 * sp.max_contacts
         keep = []
 

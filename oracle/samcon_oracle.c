@@ -50,6 +50,7 @@ typedef struct {
     /* contact persistence: warm-start factor applied to the cached normal impulse of a contact that was also present in
      * the previous sub-step (0 = stateless contacts); spinning (torsional) friction coefficients, ground / link-link */
     double warmstart, spin, spin_self;
+    int exact_box;     /* link-vs-link narrow phase: boxes as boxes (1) or as their capsule stand-ins (0, round 1) */
 } oc_model;
 
 typedef struct {
@@ -215,7 +216,7 @@ oc_model *oc_create(int nl, const int *parent, const int *jtype, const double *j
                     const double *I_pd, int ns, const int *sh_link, const int *sh_kind, const double *sh_dims,
                     const double *sh_pos, const double *sh_rot, const double *kp, const double *kd,
                     const double *maxf,
-                    const double *simp /* dt,nsub,niter,gx,gy,gz,mu,erp,cthresh,maxc,maxvel,selfcol,mu_self,warmstart,spin,spin_self */,
+                    const double *simp /* dt,nsub,niter,gx,gy,gz,mu,erp,cthresh,maxc,maxvel,selfcol,mu_self,warmstart,spin,spin_self,exact_box */,
                     const double *jw, int nee, const int *ee, const double *cw, double height) {
     if (nl > MAXL || ns > MAXS) return NULL;
     oc_model *m = (oc_model *)calloc(1, sizeof(oc_model));
@@ -244,7 +245,7 @@ oc_model *oc_create(int nl, const int *parent, const int *jtype, const double *j
     m->nee = nee; for (int k = 0; k < nee; k++) m->ee[k] = ee[k];
     memcpy(m->cw, cw, 40); m->height = height;
     m->selfcol = (int)simp[11]; m->mu_self = simp[12];
-    m->warmstart = simp[13]; m->spin = simp[14]; m->spin_self = simp[15];
+    m->warmstart = simp[13]; m->spin = simp[14]; m->spin_self = simp[15]; m->exact_box = (int)simp[16];
     self_collision_setup(m);
     return m;
 }
@@ -487,6 +488,83 @@ static void seg_seg(const double *p1, const double *q1, const double *p2, const 
     for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
 }
 
+/* Closest points of a box (half extents h, its own frame) and a segment p0 + t (p1 - p0), t in [0,1] (a sphere centre is
+ * the segment with p1 = p0).  f(t) = squared distance of the segment point to the box is convex and piecewise quadratic:
+ * safeguarded Newton on f' (each step solves the current piece exactly; a step that leaves the bracket is replaced by a
+ * bisection), a fixed number of iterations.  Returns the distance between the cores; q = point of the box, p = point of the
+ * segment.  When the segment passes through the box (distance 0) p is the middle of the part inside, q its projection onto
+ * the nearest face, *axis / *sgn name that face and the (negative) return value is minus the depth of p below it. */
+static double box_segment(const double *h, const double *p0, const double *p1, double *q, double *p, int *axis, double *sgn) {
+    double d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    double dd = dot3(d, d), t = dd > 1e-18 ? clamp01(-dot3(p0, d) / dd) : 0.0, lo = 0.0, hi = 1.0;
+    int lo_seen = 0, hi_seen = 0;          /* f' evaluated at the bracket's ends (negative at lo, positive at hi)? */
+    for (int it = 0; it < 16; it++) {
+        double g1 = 0, g2 = 0;
+        for (int i = 0; i < 3; i++) {
+            double x = p0[i] + t * d[i], o = x - fmax(-h[i], fmin(h[i], x));
+            g1 += o * d[i];
+            if (o != 0.0) g2 += d[i] * d[i];
+        }
+        if (g1 == 0 || g2 <= 0) break;
+        if (g1 > 0) { if (t <= 0.0) break; hi = t; hi_seen = 1; }          /* rising at the start of the segment: done */
+        else { if (t >= 1.0) break; lo = t; lo_seen = 1; }
+        double tn = t - g1 / g2;
+        if (tn <= lo) tn = lo_seen ? 0.5 * (lo + hi) : lo;
+        else if (tn >= hi) tn = hi_seen ? 0.5 * (lo + hi) : hi;
+        if (tn == t) break;
+        t = tn;
+    }
+    double len2 = 0;
+    for (int i = 0; i < 3; i++) { p[i] = p0[i] + t * d[i]; q[i] = fmax(-h[i], fmin(h[i], p[i])); len2 += (p[i] - q[i]) * (p[i] - q[i]); }
+    *axis = -1; *sgn = 0;
+    if (len2 > 1e-24) return sqrt(len2);
+    /* the segment enters the box: clip it against the three slabs, take the middle of what is inside */
+    double t0 = 0, t1 = 1;
+    for (int i = 0; i < 3; i++) {
+        if (fabs(d[i]) < 1e-18) continue;
+        double a = (-h[i] - p0[i]) / d[i], b = (h[i] - p0[i]) / d[i];
+        if (a > b) { double c = a; a = b; b = c; }
+        if (a > t0) t0 = a;
+        if (b < t1) t1 = b;
+    }
+    t = t1 >= t0 ? 0.5 * (t0 + t1) : t;
+    double best = 1e300;
+    for (int i = 0; i < 3; i++) {
+        p[i] = p0[i] + t * d[i]; q[i] = p[i];
+        double e = h[i] - fabs(p[i]);
+        if (e < best) { best = e; *axis = i; }
+    }
+    *sgn = p[*axis] >= 0 ? 1.0 : -1.0;
+    q[*axis] = *sgn * h[*axis];
+    return -best;
+}
+
+/* narrow phase of a pair in which shape sb is a box and the other side is the sphere-swept segment (a0, a1, ra) in world
+ * coordinates: surface points pbox / pseg (world), unit normal from the box to the segment side, signed distance */
+static int box_pair(const oc_model *m, const oc_kin *k, int sb, const double *a0, const double *a1, double ra,
+                    double *pbox, double *pseg, double *n_box_to_seg, double *dist) {
+    int lb = m->sh_link[sb];
+    double Rw[9], c[3], t[3], h[3], l0[3], l1[3], q[3], p[3], sgn;
+    int axis;
+    mm3(k->R[lb], m->sh_rot[sb], Rw);
+    mv3(k->R[lb], m->sh_pos[sb], t);
+    for (int i = 0; i < 3; i++) { c[i] = k->p[lb][i] + t[i]; h[i] = 0.5 * m->sh_dims[sb][i]; }
+    for (int i = 0; i < 3; i++) t[i] = a0[i] - c[i];
+    mtv3(Rw, t, l0);
+    for (int i = 0; i < 3; i++) t[i] = a1[i] - c[i];
+    mtv3(Rw, t, l1);
+    double len = box_segment(h, l0, l1, q, p, &axis, &sgn), nl[3];
+    if (axis >= 0) { nl[0] = nl[1] = nl[2] = 0; nl[axis] = sgn; }
+    else { if (len < 1e-9) return 0; for (int i = 0; i < 3; i++) nl[i] = (p[i] - q[i]) / len; }
+    *dist = len - ra;
+    double qs[3];
+    for (int i = 0; i < 3; i++) qs[i] = p[i] - ra * nl[i];                      /* point of the swept segment's surface */
+    mv3(Rw, nl, n_box_to_seg);
+    mv3(Rw, q, t); for (int i = 0; i < 3; i++) pbox[i] = c[i] + t[i];
+    mv3(Rw, qs, t); for (int i = 0; i < 3; i++) pseg[i] = c[i] + t[i];
+    return 1;
+}
+
 static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
     static __thread oc_contact cand[MAXCAND];
     int n = 0;
@@ -499,6 +577,23 @@ static int collide(const oc_model *m, const oc_kin *k, oc_contact *out) {
         mv3(k->R[la], m->cap_p1[sa], t); for (int a = 0; a < 3; a++) a1[a] = k->p[la][a] + t[a];
         mv3(k->R[lb], m->cap_p0[sb], t); for (int a = 0; a < 3; a++) b0[a] = k->p[lb][a] + t[a];
         mv3(k->R[lb], m->cap_p1[sb], t); for (int a = 0; a < 3; a++) b1[a] = k->p[lb][a] + t[a];
+        if (m->exact_box && (m->sh_kind[sa] == 2 || m->sh_kind[sb] == 2)) {
+            /* a box is a box; when both are, the second one is stood in for by its capsule */
+            double pbx[3], psg[3], nb2s[3], dist;
+            int a_is_box = m->sh_kind[sa] == 2;
+            int ok = a_is_box ? box_pair(m, k, sa, b0, b1, m->cap_r[sb], pbx, psg, nb2s, &dist)
+                              : box_pair(m, k, sb, a0, a1, m->cap_r[sa], pbx, psg, nb2s, &dist);
+            if (ok && dist < m->cthresh && n < MAXCAND) {
+                oc_contact *cc = &cand[n++];
+                cc->link = la; cc->link2 = lb; cc->dist = dist; cc->mu = m->mu_self; cc->spin = m->spin_self; cc->id = pi;
+                for (int a = 0; a < 3; a++) {       /* normal from the second link to the first */
+                    cc->n[a] = a_is_box ? -nb2s[a] : nb2s[a];
+                    cc->pos[a] = a_is_box ? pbx[a] : psg[a];
+                    cc->pos2[a] = a_is_box ? psg[a] : pbx[a];
+                }
+            }
+            continue;
+        }
         seg_seg(a0, a1, b0, b1, c1, c2);
         for (int a = 0; a < 3; a++) d[a] = c1[a] - c2[a];
         double len = sqrt(dot3(d, d)), dist = len - m->cap_r[sa] - m->cap_r[sb];
@@ -892,6 +987,10 @@ int oc_contacts_full(const oc_model *m, const double *state, double *out /* [max
     return n;
 }
 int oc_num_pairs(const oc_model *m) { return m->npair; }
+double oc_box_segment(const double *h, const double *p0, const double *p1, double *q, double *p, int *axis) {
+    double sgn;
+    return box_segment(h, p0, p1, q, p, axis, &sgn);
+}
 /* free dynamics with given generalised forces and no stable PD: used by conservation tests */
 void oc_step_torque(const oc_model *m, double *state, const double *tau, int nsub_total) {
     oc_state st; oc_kin k;

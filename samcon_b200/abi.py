@@ -37,6 +37,7 @@ class ScModel(C.Structure):
         ("nprim", C.c_int32), ("npair", C.c_int32), ("prim_body", i32p), ("prim", f32p), ("pair", i32p),
         ("friction_self", C.c_float), ("warmstart", C.c_float), ("spinning_friction", C.c_float),
         ("spinning_friction_self", C.c_float),
+        ("nbox", C.c_int32), ("prim_box", i32p), ("box", f32p),
     ]
 
 
@@ -76,6 +77,9 @@ def make_model(character):
     m.pair = I(t["pair"] if len(t["pair"]) else np.zeros((1, 2)))
     m.friction_self = sp.friction_self
     m.warmstart, m.spinning_friction, m.spinning_friction_self = sp.warmstart, sp.spinning_friction, sp.spinning_friction_self
+    m.nbox = len(t["box"])
+    m.prim_box = I(t["prim_box"])
+    m.box = F(t["box"] if len(t["box"]) else np.zeros((1, 15)))
     return m, keep
 
 

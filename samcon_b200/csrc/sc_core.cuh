@@ -77,13 +77,16 @@ constexpr int LPS = 32 / SC_TILE;    // lanes per sample
 static_assert(TILE * LPS == 32, "one tile per warp");
 
 // self-collision tables (part of Tables, in shared memory)
-constexpr int NPRIM = SC_MAX_PRIMS, NPAIR = SC_MAX_PAIRS;
+constexpr int NPRIM = SC_MAX_PRIMS, NPAIR = SC_MAX_PAIRS, NBOX = SC_MAX_BOXES;
 constexpr int PAIRS_PER_LANE_MAX = (NPAIR + LPS - 1) / LPS, PRIMS_PER_LANE_MAX = (NPRIM + LPS - 1) / LPS;
 struct SelfTables {
     int nprim, npair, prims_per_lane, pairs_per_lane;
     float prim[NPRIM * 8];              // sphere-swept segment in the body frame: p0, p1, radius, bounding radius about the midpoint
     float pair_r2[NPAIR];               // (bounding radius a + bounding radius b + contact threshold)^2
     unsigned char pair_a[NPAIR], pair_b[NPAIR], prim_body[NPRIM];
+    int nbox;                           // exact boxes (0: every box is its capsule stand-in `prim`)
+    signed char prim_box[NPRIM];        // box index of the primitive or -1
+    float box[NBOX * 15];               // body frame: centre (3), axes R row major with v_body = R v_box (9), half extents (3)
 };
 
 // ---- derived model tables (copied to shared memory once per CTA) ------------------------------------------
@@ -634,9 +637,90 @@ SC_DEV V3 prim_point(const float *S, const SelfTables &ST, int p, int which) {
     const float *q = ST.prim + 8 * p + 3 * which;
     return ld3(S, O_PW + 3 * b) + mul(ldM(S, O_RW + 9 * b), mk(q[0], q[1], q[2]));
 }
+// Closest points of a box (half extents h, its own frame) and the segment p0 + t (p1 - p0), t in [0,1] (a sphere centre
+// is the segment with p1 = p0): f(t) = squared distance of the segment point to the box is convex and piecewise quadratic --
+// safeguarded Newton on f' (a step solves the current piece exactly, a step that leaves the bracket becomes a bisection).
+// Returns the distance of the cores, q on the box, p on the segment.  A segment that passes through the box: p = middle of
+// the part inside, q = its projection on the nearest face (axis, sgn), return value = minus the depth of p below that face.
+SC_DEV float box_segment(V3 h, V3 p0, V3 p1, V3 &q, V3 &p, int &axis, float &sgn) {
+    const float hh[3] = {h.x, h.y, h.z}, a0[3] = {p0.x, p0.y, p0.z}, d[3] = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z};
+    const float dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    float t = dd > 1e-18f ? clamp01(-(a0[0] * d[0] + a0[1] * d[1] + a0[2] * d[2]) / dd) : 0.0f, lo = 0.0f, hi = 1.0f;
+    bool lo_seen = false, hi_seen = false;
+    for (int it = 0; it < 16; it++) {
+        float g1 = 0, g2 = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float x = a0[i] + t * d[i], o = x - fmaxf(-hh[i], fminf(hh[i], x));
+            g1 += o * d[i];
+            if (o != 0.0f) g2 += d[i] * d[i];
+        }
+        if (g1 == 0.0f || g2 <= 0.0f) break;
+        if (g1 > 0) { if (t <= 0.0f) break; hi = t; hi_seen = true; }
+        else { if (t >= 1.0f) break; lo = t; lo_seen = true; }
+        float tn = t - g1 / g2;
+        if (tn <= lo) tn = lo_seen ? 0.5f * (lo + hi) : lo;
+        else if (tn >= hi) tn = hi_seen ? 0.5f * (lo + hi) : hi;
+        if (tn == t) break;
+        t = tn;
+    }
+    float pp[3], qq[3], len2 = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { pp[i] = a0[i] + t * d[i]; qq[i] = fmaxf(-hh[i], fminf(hh[i], pp[i])); len2 += (pp[i] - qq[i]) * (pp[i] - qq[i]); }
+    axis = -1; sgn = 0;
+    if (len2 > 1e-24f) { q = mk(qq[0], qq[1], qq[2]); p = mk(pp[0], pp[1], pp[2]); return sqrtf(len2); }
+    float t0 = 0, t1 = 1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (fabsf(d[i]) < 1e-18f) continue;
+        float a = (-hh[i] - a0[i]) / d[i], b = (hh[i] - a0[i]) / d[i];
+        if (a > b) { const float c = a; a = b; b = c; }
+        t0 = fmaxf(t0, a); t1 = fminf(t1, b);
+    }
+    if (t1 >= t0) t = 0.5f * (t0 + t1);
+    float best = 3.0e38f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        pp[i] = a0[i] + t * d[i]; qq[i] = pp[i];
+        const float e = hh[i] - fabsf(pp[i]);
+        if (e < best) { best = e; axis = i; }
+    }
+    sgn = pp[axis] >= 0 ? 1.0f : -1.0f;
+    qq[axis] = sgn * hh[axis];
+    q = mk(qq[0], qq[1], qq[2]); p = mk(pp[0], pp[1], pp[2]);
+    return -best;
+}
+
 // narrow phase of one primitive pair: surface points (world), unit normal from b to a, signed distance
 SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, V3 &pa, V3 &pb, V3 &n, float &dist) {
     const int a = ST.pair_a[pr], b = ST.pair_b[pr];
+    if (ST.nbox > 0 && (ST.prim_box[a] >= 0 || ST.prim_box[b] >= 0)) {
+        // a box is a box; when both are, the second one is stood in for by its capsule
+        const bool a_is_box = ST.prim_box[a] >= 0;
+        const int pbx = a_is_box ? a : b, psg = a_is_box ? b : a, body = ST.prim_body[pbx];
+        const float *bx = ST.box + 15 * ST.prim_box[pbx];
+        const M3 Rb = ldM(S, O_RW + 9 * body);
+        M3 Rl;
+#pragma unroll
+        for (int i = 0; i < 9; i++) Rl.a[i] = bx[3 + i];
+        const M3 Rw = mul(Rb, Rl);
+        const V3 c = ld3(S, O_PW + 3 * body) + mul(Rb, mk(bx[0], bx[1], bx[2]));
+        const V3 l0 = mulT(Rw, prim_point(S, ST, psg, 0) - c), l1 = mulT(Rw, prim_point(S, ST, psg, 1) - c);
+        const float rs = ST.prim[8 * psg + 6];
+        V3 q, p;
+        int axis;
+        float sgn;
+        const float len = box_segment(mk(bx[12], bx[13], bx[14]), l0, l1, q, p, axis, sgn);
+        V3 nl;
+        if (axis >= 0) nl = mk(axis == 0 ? sgn : 0.0f, axis == 1 ? sgn : 0.0f, axis == 2 ? sgn : 0.0f);
+        else { if (len < 1e-9f) return false; nl = (1.0f / len) * (p - q); }
+        dist = len - rs;
+        const V3 nw = mul(Rw, nl);                                  // from the box to the swept segment
+        const V3 pbox = c + mul(Rw, q), pseg = c + mul(Rw, p - rs * nl);
+        n = a_is_box ? neg(nw) : nw;                                // from b to a
+        pa = a_is_box ? pbox : pseg; pb = a_is_box ? pseg : pbox;
+        return true;
+    }
     V3 c1, c2;
     seg_seg(prim_point(S, ST, a, 0), prim_point(S, ST, a, 1), prim_point(S, ST, b, 0), prim_point(S, ST, b, 1), c1, c2);
     const V3 d = c1 - c2;

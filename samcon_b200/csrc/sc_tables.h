@@ -88,6 +88,19 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
             const double dx = q[3] - q[0], dy = q[4] - q[1], dz = q[5] - q[2];
             ST->prim[8 * p + 7] = (float)(q[6] + 0.5 * sqrt(dx * dx + dy * dy + dz * dz));
         }
+        if (m->nbox < 0 || m->nbox > SC_MAX_BOXES || (m->nbox > 0 && (!m->prim_box || !m->box))) SC_FAIL("nbox=%d outside 0..%d", m->nbox, SC_MAX_BOXES);
+        ST->nbox = m->nbox;
+        for (int p = 0; p < m->nprim; p++) {
+            const int bx = m->nbox > 0 ? m->prim_box[p] : -1;
+            if (bx >= m->nbox) SC_FAIL("bad prim_box");
+            ST->prim_box[p] = (signed char)(bx < 0 ? -1 : bx);
+            if (bx >= 0) {
+                const auto *q = m->box + 15 * bx;
+                for (int k = 0; k < 15; k++) ST->box[15 * bx + k] = q[k];
+                // the broad phase's bounding sphere has to hold the box, not just its capsule stand-in
+                ST->prim[8 * p + 7] = (float)sqrt((double)q[12] * q[12] + (double)q[13] * q[13] + (double)q[14] * q[14]);
+            }
+        }
         for (int i = 0; i < m->npair; i++) {
             const int a = m->pair[2 * i], b = m->pair[2 * i + 1];
             if (a < 0 || b < 0 || a >= m->nprim || b >= m->nprim) SC_FAIL("bad pair %d", i);

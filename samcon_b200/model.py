@@ -55,6 +55,10 @@ class SimParams:
     # registers and sc_create rejects a non-zero value).
     spinning_friction: float = 0.0
     spinning_friction_self: float = 0.0
+    # link-vs-link narrow phase: a box (feet, upper arms, forearms: humanoid.urdf:76,126,248,268,316,336) against a sphere or
+    # capsule is the exact box-to-swept-segment distance; of two boxes the second is stood in for by its capsule.  False =
+    # round 1: every box is its capsule stand-in.
+    exact_box_contacts: bool = True
 
 
 def _skew(v):
@@ -309,15 +313,22 @@ class Character:
         cand = np.array(cand, dtype=np.float64)
         # self-collision primitives (one per URDF shape, in shape order) in the frame of the moving body that carries
         # the shape's link, and the primitive pairs that may touch
-        prim_body, prim = [], []
+        prim_body, prim, prim_box, boxes = [], [], [], []
         for i, l in enumerate(L):
             for s in l.shapes:
                 p0, p1, r = shape_capsule(s)
                 prim_body.append(body_of_link[owner[i]])
                 prim.append([*(off[i] + p0), *(off[i] + p1), r])
+                if s.kind == BOX and self.sim.exact_box_contacts:
+                    # the box itself, in the frame of the moving body: centre, axes (v_body = R v_box, row major), half extents
+                    prim_box.append(len(boxes))
+                    boxes.append([*(off[i] + s.pos), *s.rot.reshape(9), *(0.5 * s.dims)])
+                else:
+                    prim_box.append(-1)
         pair = np.array(self_collision_pairs(L), dtype=np.int32).reshape(-1, 2)
         return {
             "prim_body": np.array(prim_body, dtype=np.int32), "prim": np.array(prim, dtype=np.float64), "pair": pair,
+            "prim_box": np.array(prim_box, dtype=np.int32), "box": np.array(boxes, dtype=np.float64).reshape(-1, 15),
             "nb": nb, "nlev": nlev, "level_start": np.array(level_start, dtype=np.int32),
             "parent": parent, "jidx": jidx, "jorg": jorg, "kp": kp, "kd": kd, "maxf": maxf,
             "inertia_dyn": inert["dyn"], "inertia_pd": inert["pd"],

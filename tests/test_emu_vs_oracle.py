@@ -194,3 +194,57 @@ def test_warmstart_off_matches_stateless_oracle(emu, walk_cfg):
     again, _, _ = _window(emu, ch, st, actions, target, 20, parent_cache=cache)
     cold, _, _ = _window(emu, ch, st, actions, target, 20)
     np.testing.assert_array_equal(again, cold)                                      # without warm start the cache is inert
+
+
+def _box_vs_round_poses(oracle, n, seed=5):
+    """Seeded search for airborne poses (random left leg and arms) in which a box link -- a foot, an upper arm, a forearm --
+    is within the contact margin of a capsule / sphere link that is not its ancestor (found: the left foot's box against the
+    right shin's capsule)."""
+    from helpers import rand_quat
+    rng = np.random.default_rng(seed)
+    boxes = {3, 6, 13, 14, 17, 18}                           # URDF link indices of the box links
+    out = []
+    while len(out) < n:
+        s = stand(rng, 0.0, 0.0, 2.0)
+        s[0:2] = 0
+        for j in (0, 1, 2, 12, 13, 15, 16):
+            s[7 + 4 * j:11 + 4 * j] = rand_quat(rng, 1.2)
+        c = oracle.contacts_full(s)
+        c = c[c[:, 1] >= 0]
+        if any((int(r[0]) in boxes) != (int(r[1]) in boxes) and -0.02 < r[11] < 0.015 for r in c):
+            out.append(s)
+    return np.array(out)
+
+
+def test_box_contacts_exact_narrow_phase(emu, character, oracle):
+    """Link-vs-link pairs with a box (SimParams.exact_box_contacts): a foot box against the other leg's shin capsule (box vs
+    swept segment, exact) and feet against each other (box vs box: the second as its capsule) -- the kernel's float32
+    safeguarded Newton against the oracle's float64 one."""
+    from helpers import legs_crossed
+    rng = np.random.default_rng(13)
+    parents = np.concatenate([_box_vs_round_poses(oracle, 6), np.array([legs_crossed(rng, 0.10 + 0.02 * i, 2.0, 0.05) for i in range(2)])])
+    # PD targets = the poses themselves, slightly perturbed: the touching links keep pressing / sliding on each other
+    actions = np.array([near_action(p, rng, 0.05) for p in parents])
+    target = stand(rng)
+    boxes = {3, 6, 13, 14, 17, 18}
+    seen = set()
+    for p, a in zip(parents, actions):
+        for t in (0, 20, 50):
+            c = oracle.contacts_full(oracle.step(p, a, t) if t else p)
+            for r in c[c[:, 1] >= 0]:
+                la, lb = int(r[0]), int(r[1])
+                seen.add("box-vs-box" if la in boxes and lb in boxes else "box-vs-round" if (la in boxes) != (lb in boxes) else "round")
+    assert {"box-vs-round", "box-vs-box"} <= seen, seen
+    st, cost, info = _window(emu, character, parents, actions, target, 100)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
+    rms = joint_rms(st, ost)
+    print("box contact windows: joint rms", rms)
+    assert rms.max() < 1e-3
+    np.testing.assert_allclose(cost, ocost, rtol=1e-3)
+    # the capsule stand-in of round 1 is a different model: the switch changes these windows
+    from oracle.oracle import Oracle
+    from samcon_b200.config import Config
+    from samcon_b200.model import Character, SimParams
+    o1 = Oracle(Character.from_config(Config("walk"), SimParams(exact_box_contacts=False)))
+    ost1, _, _ = o1.window(parents, actions, target, 100)
+    assert joint_rms(ost1, ost).max() > 1e-3

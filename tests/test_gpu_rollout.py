@@ -296,3 +296,20 @@ def test_two_handles_and_a_side_stream(character, pool, oracle):
         assert idx[0].tolist() == torch.argsort(ref[1], stable=True)[:6].tolist()
     finally:
         other.close()
+
+
+def test_box_contacts_exact_narrow_phase(pool, oracle):
+    """Link-vs-link pairs with a box on the GPU (exact box vs swept-segment narrow phase; of two boxes the second as its
+    capsule): a foot box against the other shin, feet against each other."""
+    from helpers import legs_crossed
+    from test_emu_vs_oracle import _box_vs_round_poses
+    rng = np.random.default_rng(13)
+    parents = np.concatenate([_box_vs_round_poses(oracle, 12), np.array([legs_crossed(rng, 0.10 + 0.01 * i, 2.0, 0.05) for i in range(4)])])
+    actions = np.array([near_action(p, rng, 0.05) for p in parents])
+    target = stand(rng)
+    st, cost, info = _run(pool, parents, actions, target, 100, 1)
+    ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
+    rms = joint_rms(st, ost)
+    print(f"box contact windows: joint rms median {np.median(rms):.2e} max {rms.max():.2e}")
+    assert rms.max() < JOINT_TOL
+    np.testing.assert_allclose(cost, ocost, rtol=COST_RTOL)

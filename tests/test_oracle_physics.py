@@ -233,3 +233,64 @@ def test_standing_ground_reaction_carries_the_weight(oracle, character):
     weight = sum(l.mass for l in character.links) * 9.8
     assert abs(imp[:, 2].mean() / h - weight) / weight < 0.01
     assert np.abs(imp[:, :2].mean(axis=0) / h).max() < 0.1 * weight < character.sim.friction * weight
+
+
+def test_box_segment_closest_points_against_brute_force():
+    """The exact box narrow phase (link-vs-link pairs with a foot / arm box): closest points of a box and a segment by
+    safeguarded Newton on the convex piecewise-quadratic distance, against a dense scan; degenerate segments (spheres);
+    segments through the box report the depth below the nearest face at the middle of the part inside."""
+    import ctypes as C
+    from oracle.oracle import lib
+    L = lib()
+    L.oc_box_segment.restype = C.c_double
+    rng = np.random.default_rng(17)
+
+    def call(h, p0, p1):
+        q, p = np.zeros(3), np.zeros(3)
+        ax = C.c_int(0)
+        P = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.POINTER(C.c_double))
+        d = L.oc_box_segment(P(h), P(p0), P(p1), q.ctypes.data_as(C.POINTER(C.c_double)), p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ax))
+        return d, q, p, ax.value
+
+    ts = np.linspace(0, 1, 20001)
+    worst = 0.0
+    for _ in range(300):
+        h = rng.uniform(0.02, 0.15, 3)
+        p0 = rng.uniform(-0.4, 0.4, 3)
+        p1 = p0 if rng.random() < 0.2 else p0 + rng.uniform(-0.4, 0.4, 3)
+        pts = p0[None] + ts[:, None] * (p1 - p0)[None]
+        dist = np.linalg.norm(pts - np.clip(pts, -h, h), axis=1)
+        d, q, p, ax = call(h, p0, p1)
+        if dist.min() > 1e-9:
+            assert ax == -1
+            assert abs(d - dist.min()) < 2e-5 * max(1.0, dist.min()) + 1e-9                  # the scan's grid is the coarser one
+            assert d <= dist.min() + 1e-8
+            np.testing.assert_allclose(np.linalg.norm(p - q), d, atol=1e-12)
+            assert np.all(np.abs(q) <= h + 1e-12)
+            worst = max(worst, abs(d - dist.min()))
+        else:
+            inside = np.all(np.abs(pts) <= h, axis=1)
+            assert ax >= 0 and d <= 0 and np.all(np.abs(p) <= h + 1e-9)
+            np.testing.assert_allclose(-d, (h - np.abs(p)).min(), atol=1e-12)                # depth below the nearest face
+            tm = 0.5 * (ts[inside][0] + ts[inside][-1])
+            np.testing.assert_allclose(p, p0 + tm * (p1 - p0), atol=2e-4)                    # middle of the part inside
+    assert worst < 1e-5
+
+
+def test_exact_box_contacts_switch(walk_cfg):
+    """exact_box_contacts: feet interpenetrating sideways (box-box: the first box exact, the second its capsule) and an arm
+    box against the torso spheres give contacts whose points lie on the box surface; the capsule stand-in of round 1 is
+    still there behind the switch."""
+    from helpers import legs_crossed
+    from oracle.oracle import Oracle
+    from samcon_b200.model import Character, SimParams
+    rng = np.random.default_rng(9)
+    s = legs_crossed(rng, 0.12, 2.0, 0.0)
+    exact = Oracle(Character.from_config(walk_cfg, SimParams(exact_box_contacts=True))).contacts_full(s)
+    standin = Oracle(Character.from_config(walk_cfg, SimParams(exact_box_contacts=False))).contacts_full(s)
+    feet = lambda c: c[(c[:, 0] == 3) & (c[:, 1] == 6)]                       # lankle (link 3) vs rankle (link 6)
+    assert len(feet(exact)) == 1 and len(feet(standin)) == 1
+    assert abs(feet(exact)[0, 11] - feet(standin)[0, 11]) > 1e-3              # the two models differ by millimetres ...
+    assert abs(feet(exact)[0, 11] - feet(standin)[0, 11]) < 2e-2              # ... not more
+    other = lambda c: c[~((c[:, 0] == 3) & (c[:, 1] == 6))]
+    np.testing.assert_allclose(other(exact), other(standin), atol=1e-12)      # capsule-capsule pairs are untouched
