@@ -511,7 +511,7 @@ static double box_segment(const double *h, const double *p0, const double *p1, d
         double tn = t - g1 / g2;
         if (tn <= lo) tn = lo_seen ? 0.5 * (lo + hi) : lo;
         else if (tn >= hi) tn = hi_seen ? 0.5 * (lo + hi) : hi;
-        if (tn == t) break;
+        if (fabs(tn - t) < 1e-15) { t = tn; break; }
         t = tn;
     }
     double len2 = 0;

@@ -87,6 +87,8 @@ struct SelfTables {
     int nbox;                           // exact boxes (0: every box is its capsule stand-in `prim`)
     signed char prim_box[NPRIM];        // box index of the primitive or -1
     float box[NBOX * 15];               // body frame: centre (3), axes R row major with v_body = R v_box (9), half extents (3)
+    float box_core[NBOX * 7];           // the box's long axis as a segment (p0, p1, body frame) and the radius of the capsule
+                                        // around it that CONTAINS the box: a cheap lower bound of any distance to the box
 };
 
 // ---- derived model tables (copied to shared memory once per CTA) ------------------------------------------
@@ -661,7 +663,7 @@ SC_DEV float box_segment(V3 h, V3 p0, V3 p1, V3 &q, V3 &p, int &axis, float &sgn
         float tn = t - g1 / g2;
         if (tn <= lo) tn = lo_seen ? 0.5f * (lo + hi) : lo;
         else if (tn >= hi) tn = hi_seen ? 0.5f * (lo + hi) : hi;
-        if (tn == t) break;
+        if (fabsf(tn - t) < 1e-7f) { t = tn; break; }
         t = tn;
     }
     float pp[3], qq[3], len2 = 0;
@@ -692,21 +694,37 @@ SC_DEV float box_segment(V3 h, V3 p0, V3 p1, V3 &q, V3 &p, int &axis, float &sgn
 }
 
 // narrow phase of one primitive pair: surface points (world), unit normal from b to a, signed distance
-SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, V3 &pa, V3 &pb, V3 &n, float &dist) {
+SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, float margin, V3 &pa, V3 &pb, V3 &n, float &dist) {
     const int a = ST.pair_a[pr], b = ST.pair_b[pr];
     if (ST.nbox > 0 && (ST.prim_box[a] >= 0 || ST.prim_box[b] >= 0)) {
         // a box is a box; when both are, the second one is stood in for by its capsule
         const bool a_is_box = ST.prim_box[a] >= 0;
         const int pbx = a_is_box ? a : b, psg = a_is_box ? b : a, body = ST.prim_body[pbx];
-        const float *bx = ST.box + 15 * ST.prim_box[pbx];
+        const float *bx = ST.box + 15 * ST.prim_box[pbx], *core = ST.box_core + 7 * ST.prim_box[pbx];
         const M3 Rb = ldM(S, O_RW + 9 * body);
+        const V3 s0 = prim_point(S, ST, psg, 0), s1 = prim_point(S, ST, psg, 1);
+        const float rs = ST.prim[8 * psg + 6];
+        {
+            // most pairs that pass the bounding spheres are still centimetres apart (an arm hanging next to the torso): the
+            // capsule that contains the box says so in closed form, and the exact routine below is only run for the rest
+            const V3 o = ld3(S, O_PW + 3 * body);
+            const V3 k0 = o + mul(Rb, mk(core[0], core[1], core[2])), k1 = o + mul(Rb, mk(core[3], core[4], core[5]));
+            V3 c1, c2;
+            seg_seg(k0, k1, s0, s1, c1, c2);
+            const V3 dl = c1 - c2, ax = k1 - k0, rr = k0 - s0;
+            // (seg_seg settles (nearly) parallel segments at an end point, which can overestimate their distance: the distance
+            // of the two LINES never does)
+            const float aa = dot(ax, ax), ra = dot(rr, ax);
+            const float d2 = fminf(dot(dl, dl), fmaxf(0.0f, dot(rr, rr) - ra * ra / fmaxf(aa, 1e-18f)));
+            const float lower = margin + core[6] + rs;
+            if (d2 >= lower * lower) return false;
+        }
         M3 Rl;
 #pragma unroll
         for (int i = 0; i < 9; i++) Rl.a[i] = bx[3 + i];
         const M3 Rw = mul(Rb, Rl);
         const V3 c = ld3(S, O_PW + 3 * body) + mul(Rb, mk(bx[0], bx[1], bx[2]));
-        const V3 l0 = mulT(Rw, prim_point(S, ST, psg, 0) - c), l1 = mulT(Rw, prim_point(S, ST, psg, 1) - c);
-        const float rs = ST.prim[8 * psg + 6];
+        const V3 l0 = mulT(Rw, s0 - c), l1 = mulT(Rw, s1 - c);
         V3 q, p;
         int axis;
         float sgn;
@@ -750,7 +768,7 @@ SC_DEV void write_contact(float *S, const Tables &T, const SelfTables &ST, int j
         const int ba = ST.prim_body[ST.pair_a[pr]], bb = ST.prim_body[ST.pair_b[pr]];
         V3 pa, pb, n;
         float d;
-        pair_contact(S, ST, pr, pa, pb, n, d);
+        pair_contact(S, ST, pr, 1.0e18f, pa, pb, n, d);
         F(O_CB + j) = i2f(ba | ((bb + 1) << 8));
         st3(S, O_CR + 3 * j, pa - ld3(S, O_PW + 3 * ba));
         st3(S, O_CR2 + 3 * j, pb - ld3(S, O_PW + 3 * bb));
@@ -816,7 +834,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
             const int pr = slot * ST.pairs_per_lane + i;
             V3 pa, pb, n;
             float dist;
-            if (pair_contact(S, ST, pr, pa, pb, n, dist)) {
+            if (pair_contact(S, ST, pr, T.cthresh, pa, pb, n, dist)) {
                 F(O_ZC + pr) = dist;
                 hits += (dist < T.cthresh ? 1 : 0) + (dist <= 0.0f ? 1 << 16 : 0);
             }

@@ -99,6 +99,17 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
                 for (int k = 0; k < 15; k++) ST->box[15 * bx + k] = q[k];
                 // the broad phase's bounding sphere has to hold the box, not just its capsule stand-in
                 ST->prim[8 * p + 7] = (float)sqrt((double)q[12] * q[12] + (double)q[13] * q[13] + (double)q[14] * q[14]);
+                // the capsule around the long axis that contains the box
+                int kx = 0;
+                for (int k = 1; k < 3; k++) if (q[12 + k] > q[12 + kx]) kx = k;
+                double rc = 0;
+                for (int k = 0; k < 3; k++) {
+                    const double ax = (double)q[3 + 3 * k + kx] * q[12 + kx];          // column kx of R, scaled by the half length
+                    ST->box_core[7 * bx + k] = (float)(q[k] + ax);
+                    ST->box_core[7 * bx + 3 + k] = (float)(q[k] - ax);
+                    if (k != kx) rc += (double)q[12 + k] * q[12 + k];
+                }
+                ST->box_core[7 * bx + 6] = (float)(sqrt(rc) * 1.0001);
             }
         }
         for (int i = 0; i < m->npair; i++) {

@@ -132,7 +132,9 @@ def test_self_contact_window(pool, oracle):
     from helpers import legs_crossed
     rng = np.random.default_rng(7)
     n = 24
-    parents = np.array([legs_crossed(rng, 0.03 + 0.004 * i, 2.0 if i % 2 else 0.995, 0.1) for i in range(n)])
+    # (up to 0.1 rad: beyond that the feet's boxes pass through each other's cores, where the nearest-face choice of any
+    # penetration-depth rule flips on rounding)
+    parents = np.array([legs_crossed(rng, 0.03 + 0.003 * i, 2.0 if i % 2 else 0.995, 0.1) for i in range(n)])
     actions = np.array([legs_crossed(rng, 0.3 + 0.008 * i)[7:75] for i in range(n)])
     target = stand(rng)
     n_self = sum((oracle.contacts_full(oracle.step(p, a, 60))[:, 1] >= 0).sum() for p, a in zip(parents[:8], actions[:8]))
