@@ -15,7 +15,7 @@ namespace cg = cooperative_groups;
 // ============================================================================================================
 constexpr int TABLE_WORDS = (sizeof(Tables) + 15) / 16 * 4;
 
-template <int WPB>
+template <int WPB, class TT>
 __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *__restrict__ gT, RolloutArgs a) {
     extern __shared__ __align__(16) float smem[];
     {
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *_
         for (int i = threadIdx.x; i < TABLE_WORDS / 4; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const Tables &T = *reinterpret_cast<const Tables *>(smem);
+    const TT &T = *reinterpret_cast<const TT *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *sm = smem + TABLE_WORDS + warp * WORDS_PER_TILE;
     const int ntiles = (a.S + TILE - 1) / TILE;
@@ -481,10 +481,11 @@ extern "C" int sc_create(sc_handle *out, const sc_model *model, int device) {
     SC_CUDA(h, cudaMemset(h->d_tables, 0, TABLE_WORDS * 4));
     SC_CUDA(h, cudaMemcpy(h->d_tables, &h->h_tables, sizeof(Tables), cudaMemcpyHostToDevice));
     h->smem_bytes = (TABLE_WORDS + WPB * WORDS_PER_TILE) * 4;
-    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesCapsule>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesBox>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     int nsm = 0, per_sm = 0;
     SC_CUDA(h, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-    SC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc_rollout_kernel<WPB>, 32 * WPB, h->smem_bytes));
+    SC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc_rollout_kernel<WPB, TablesBox>, 32 * WPB, h->smem_bytes));
     if (per_sm < 1) return sc_fail(h, SC_ECUDA, "rollout kernel does not fit an SM (%d B shared)", h->smem_bytes);
     h->grid_cap = nsm * per_sm;
     int sel_per_sm = 0;
@@ -563,9 +564,11 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a, cudaStream_t s
     RolloutArgs ap = a;
     if (!h->d_prof) { cudaMalloc(&h->d_prof, SC_NPHASE * sizeof(long long)); cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long)); }
     ap.prof = a.nsteps > 0 ? h->d_prof : nullptr;
-    sc_rollout_kernel<WPB><<<grid, threads, smem, st>>>(h->d_tables, ap);
+    if (h->h_tables.self.nbox > 0) sc_rollout_kernel<WPB, TablesBox><<<grid, threads, smem, st>>>(h->d_tables, ap);
+    else sc_rollout_kernel<WPB, TablesCapsule><<<grid, threads, smem, st>>>(h->d_tables, ap);
 #else
-    sc_rollout_kernel<WPB><<<grid, threads, smem, st>>>(h->d_tables, a);
+    if (h->h_tables.self.nbox > 0) sc_rollout_kernel<WPB, TablesBox><<<grid, threads, smem, st>>>(h->d_tables, a);
+    else sc_rollout_kernel<WPB, TablesCapsule><<<grid, threads, smem, st>>>(h->d_tables, a);
 #endif
     h->launches++;
     SC_CUDA(h, cudaGetLastError());

@@ -104,6 +104,10 @@ struct Tables {
     float height, dt, h, g[3], mu, mu_self, erp, cthresh, maxvel, inv_total_mass, warmstart;
     SelfTables self;
 };
+// The same tables under two static types: the rollout is compiled twice, with and without the exact box narrow phase, so
+// that the default (boxes as their capsule stand-ins) does not carry -- or fetch -- the code of a routine it never runs.
+struct TablesCapsule : Tables { static constexpr bool BOX = false; };
+struct TablesBox : Tables { static constexpr bool BOX = true; };
 
 
 // ---- per-sample shared-memory layout (32-bit words) --------------------------------------------------------
@@ -645,58 +649,55 @@ SC_DEV V3 prim_point(const float *S, const SelfTables &ST, int p, int which) {
 // Returns the distance of the cores, q on the box, p on the segment.  A segment that passes through the box: p = middle of
 // the part inside, q = its projection on the nearest face (axis, sgn), return value = minus the depth of p below that face.
 SC_DEV float box_segment(V3 h, V3 p0, V3 p1, V3 &q, V3 &p, int &axis, float &sgn) {
-    const float hh[3] = {h.x, h.y, h.z}, a0[3] = {p0.x, p0.y, p0.z}, d[3] = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z};
-    const float dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-    float t = dd > 1e-18f ? clamp01(-(a0[0] * d[0] + a0[1] * d[1] + a0[2] * d[2]) / dd) : 0.0f, lo = 0.0f, hi = 1.0f;
+    // (scalars throughout: an array indexed by the exit axis would put every operand of the Newton loop into local memory)
+    const V3 d = p1 - p0;
+    const float dd = dot(d, d);
+    float t = dd > 1e-18f ? clamp01(-dot(p0, d) / dd) : 0.0f, lo = 0.0f, hi = 1.0f;
     bool lo_seen = false, hi_seen = false;
-    for (int it = 0; it < 16; it++) {
-        float g1 = 0, g2 = 0;
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const float x = a0[i] + t * d[i], o = x - fmaxf(-hh[i], fminf(hh[i], x));
-            g1 += o * d[i];
-            if (o != 0.0f) g2 += d[i] * d[i];
-        }
+    for (int it = 0; it < 8; it++) {
+        const V3 x = p0 + t * d;
+        const V3 o = mk(x.x - fmaxf(-h.x, fminf(h.x, x.x)), x.y - fmaxf(-h.y, fminf(h.y, x.y)), x.z - fmaxf(-h.z, fminf(h.z, x.z)));
+        const float g1 = dot(o, d);
+        const float g2 = (o.x != 0.0f ? d.x * d.x : 0.0f) + (o.y != 0.0f ? d.y * d.y : 0.0f) + (o.z != 0.0f ? d.z * d.z : 0.0f);
         if (g1 == 0.0f || g2 <= 0.0f) break;
         if (g1 > 0) { if (t <= 0.0f) break; hi = t; hi_seen = true; }
         else { if (t >= 1.0f) break; lo = t; lo_seen = true; }
         float tn = t - g1 / g2;
         if (tn <= lo) tn = lo_seen ? 0.5f * (lo + hi) : lo;
         else if (tn >= hi) tn = hi_seen ? 0.5f * (lo + hi) : hi;
-        if (fabsf(tn - t) < 1e-7f) { t = tn; break; }
+        if (fabsf(tn - t) < 1e-6f) { t = tn; break; }
         t = tn;
     }
-    float pp[3], qq[3], len2 = 0;
-#pragma unroll
-    for (int i = 0; i < 3; i++) { pp[i] = a0[i] + t * d[i]; qq[i] = fmaxf(-hh[i], fminf(hh[i], pp[i])); len2 += (pp[i] - qq[i]) * (pp[i] - qq[i]); }
+    p = p0 + t * d;
+    q = mk(fmaxf(-h.x, fminf(h.x, p.x)), fmaxf(-h.y, fminf(h.y, p.y)), fmaxf(-h.z, fminf(h.z, p.z)));
+    const V3 e = p - q;
+    const float len2 = dot(e, e);
     axis = -1; sgn = 0;
-    if (len2 > 1e-24f) { q = mk(qq[0], qq[1], qq[2]); p = mk(pp[0], pp[1], pp[2]); return sqrtf(len2); }
+    if (len2 > 1e-24f) return sqrtf(len2);
+    // the segment enters the box: clip it against the three slabs, take the middle of what is inside
     float t0 = 0, t1 = 1;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        if (fabsf(d[i]) < 1e-18f) continue;
-        float a = (-hh[i] - a0[i]) / d[i], b = (hh[i] - a0[i]) / d[i];
-        if (a > b) { const float c = a; a = b; b = c; }
-        t0 = fmaxf(t0, a); t1 = fminf(t1, b);
-    }
+    if (fabsf(d.x) >= 1e-18f) { const float a = (-h.x - p0.x) / d.x, b = (h.x - p0.x) / d.x; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+    if (fabsf(d.y) >= 1e-18f) { const float a = (-h.y - p0.y) / d.y, b = (h.y - p0.y) / d.y; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+    if (fabsf(d.z) >= 1e-18f) { const float a = (-h.z - p0.z) / d.z, b = (h.z - p0.z) / d.z; t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
     if (t1 >= t0) t = 0.5f * (t0 + t1);
-    float best = 3.0e38f;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        pp[i] = a0[i] + t * d[i]; qq[i] = pp[i];
-        const float e = hh[i] - fabsf(pp[i]);
-        if (e < best) { best = e; axis = i; }
-    }
-    sgn = pp[axis] >= 0 ? 1.0f : -1.0f;
-    qq[axis] = sgn * hh[axis];
-    q = mk(qq[0], qq[1], qq[2]); p = mk(pp[0], pp[1], pp[2]);
+    p = p0 + t * d;
+    q = p;
+    const float ex = h.x - fabsf(p.x), ey = h.y - fabsf(p.y), ez = h.z - fabsf(p.z);
+    float best = ex;
+    axis = 0;
+    if (ey < best) { best = ey; axis = 1; }
+    if (ez < best) { best = ez; axis = 2; }
+    const float pc = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+    sgn = pc >= 0 ? 1.0f : -1.0f;
+    if (axis == 0) q.x = sgn * h.x; else if (axis == 1) q.y = sgn * h.y; else q.z = sgn * h.z;
     return -best;
 }
 
 // narrow phase of one primitive pair: surface points (world), unit normal from b to a, signed distance
+template <bool BOX>
 SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, float margin, V3 &pa, V3 &pb, V3 &n, float &dist) {
     const int a = ST.pair_a[pr], b = ST.pair_b[pr];
-    if (ST.nbox > 0 && (ST.prim_box[a] >= 0 || ST.prim_box[b] >= 0)) {
+    if (BOX && ST.nbox > 0 && (ST.prim_box[a] >= 0 || ST.prim_box[b] >= 0)) {
         // a box is a box; when both are, the second one is stood in for by its capsule
         const bool a_is_box = ST.prim_box[a] >= 0;
         const int pbx = a_is_box ? a : b, psg = a_is_box ? b : a, body = ST.prim_body[pbx];
@@ -716,15 +717,24 @@ SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, float mar
             // of the two LINES never does)
             const float aa = dot(ax, ax), ra = dot(rr, ax);
             const float d2 = fminf(dot(dl, dl), fmaxf(0.0f, dot(rr, rr) - ra * ra / fmaxf(aa, 1e-18f)));
-            const float lower = margin + core[6] + rs;
+            const float lower = margin + fabsf(core[6]) + rs;
             if (d2 >= lower * lower) return false;
         }
-        M3 Rl;
+        M3 Rw = Rb;
+        if (core[6] < 0.0f) {               // (flag in the sign of the bound: the box is rotated in its body's frame)
+            M3 Rl;
 #pragma unroll
-        for (int i = 0; i < 9; i++) Rl.a[i] = bx[3 + i];
-        const M3 Rw = mul(Rb, Rl);
+            for (int i = 0; i < 9; i++) Rl.a[i] = bx[3 + i];
+            Rw = mul(Rb, Rl);
+        }
         const V3 c = ld3(S, O_PW + 3 * body) + mul(Rb, mk(bx[0], bx[1], bx[2]));
         const V3 l0 = mulT(Rw, s0 - c), l1 = mulT(Rw, s1 - c);
+        {
+            // second bound, in the box's own frame: the segment's extent against the box grown by margin + radius, axis by axis
+            const float g = margin + rs;
+            if (fminf(l0.x, l1.x) > bx[12] + g || fmaxf(l0.x, l1.x) < -bx[12] - g || fminf(l0.y, l1.y) > bx[13] + g ||
+                fmaxf(l0.y, l1.y) < -bx[13] - g || fminf(l0.z, l1.z) > bx[14] + g || fmaxf(l0.z, l1.z) < -bx[14] - g) return false;
+        }
         V3 q, p;
         int axis;
         float sgn;
@@ -739,6 +749,7 @@ SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, float mar
         pa = a_is_box ? pbox : pseg; pb = a_is_box ? pseg : pbox;
         return true;
     }
+
     V3 c1, c2;
     seg_seg(prim_point(S, ST, a, 0), prim_point(S, ST, a, 1), prim_point(S, ST, b, 0), prim_point(S, ST, b, 1), c1, c2);
     const V3 d = c1 - c2;
@@ -754,7 +765,8 @@ SC_DEV bool pair_contact(const float *S, const SelfTables &ST, int pr, float mar
 // u = unified candidate index: primitive pair u < npair, else ground point u - npair.  Link-vs-link contacts come first in
 // the contact list: a column only evaluates the rows at or after its own contact, so the (few) two-body columns pay for
 // the two-body rows and the ground columns never walk to a second body.
-SC_DEV void write_contact(float *S, const Tables &T, const SelfTables &ST, int j, int u, float z) {
+template <class TT>
+SC_DEV void write_contact(float *S, const TT &T, const SelfTables &ST, int j, int u, float z) {
     if (u >= ST.npair) {
         const int c = u - ST.npair, b = T.cand_body[c];
         const float *pt = T.cand + 4 * c;
@@ -768,7 +780,7 @@ SC_DEV void write_contact(float *S, const Tables &T, const SelfTables &ST, int j
         const int ba = ST.prim_body[ST.pair_a[pr]], bb = ST.prim_body[ST.pair_b[pr]];
         V3 pa, pb, n;
         float d;
-        pair_contact(S, ST, pr, 1.0e18f, pa, pb, n, d);
+        pair_contact<TT::BOX>(S, ST, pr, 1.0e18f, pa, pb, n, d);
         F(O_CB + j) = i2f(ba | ((bb + 1) << 8));
         st3(S, O_CR + 3 * j, pa - ld3(S, O_PW + 3 * ba));
         st3(S, O_CR2 + 3 * j, pb - ld3(S, O_PW + 3 * bb));
@@ -834,7 +846,7 @@ SC_PHASE void collide(float *sm, const TT &T, const SelfTables &ST, int L0, int 
             const int pr = slot * ST.pairs_per_lane + i;
             V3 pa, pb, n;
             float dist;
-            if (pair_contact(S, ST, pr, T.cthresh, pa, pb, n, dist)) {
+            if (pair_contact<TT::BOX>(S, ST, pr, T.cthresh, pa, pb, n, dist)) {
                 F(O_ZC + pr) = dist;
                 hits += (dist < T.cthresh ? 1 : 0) + (dist <= 0.0f ? 1 << 16 : 0);
             }

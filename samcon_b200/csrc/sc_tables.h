@@ -110,6 +110,10 @@ inline int build_tables(const sc_model *m, Tables *T, char *err, size_t errlen) 
                     if (k != kx) rc += (double)q[12 + k] * q[12 + k];
                 }
                 ST->box_core[7 * bx + 6] = (float)(sqrt(rc) * 1.0001);
+                // a box whose axes are not its body's carries the flag "rotated" in the sign of this bound
+                bool ident = true;
+                for (int k = 0; k < 9; k++) if (fabs((double)q[3 + k] - (k % 4 == 0 ? 1.0 : 0.0)) > 1e-7) ident = false;
+                if (!ident) ST->box_core[7 * bx + 6] = -ST->box_core[7 * bx + 6];
             }
         }
         for (int i = 0; i < m->npair; i++) {

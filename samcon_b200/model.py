@@ -55,10 +55,13 @@ class SimParams:
     # registers and sc_create rejects a non-zero value).
     spinning_friction: float = 0.0
     spinning_friction_self: float = 0.0
-    # link-vs-link narrow phase: a box (feet, upper arms, forearms: humanoid.urdf:76,126,248,268,316,336) against a sphere or
-    # capsule is the exact box-to-swept-segment distance; of two boxes the second is stood in for by its capsule.  False =
-    # round 1: every box is its capsule stand-in.
-    exact_box_contacts: bool = True
+    # link-vs-link narrow phase: True = a box (feet, upper arms, forearms: humanoid.urdf:76,126,248,268,316,336) against a
+    # sphere or capsule is the exact box-to-swept-segment distance, and of two boxes the second is stood in for by its capsule;
+    # False = every box is its capsule stand-in (one closed-form segment-segment distance per pair).  Off by default: on the
+    # bench workload the exact routine costs 9-10 % of the window (profiles/r2y_exact_box_cost.log) -- a lane or two per warp
+    # run it while the rest of the CTA waits at the phase barrier -- for contacts that mostly occur between the tangled legs
+    # of samples the search discards.  Oracle and kernel implement both; the parity tests cover both.
+    exact_box_contacts: bool = False
 
 
 def _skew(v):

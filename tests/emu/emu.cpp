@@ -10,7 +10,7 @@ int emu_window(const sc_model *m, const float *parents, int E, const int *parent
                const float *actions, const float *targets, int nseq, const int *sample_seq, int S, int nsteps,
                float *out_state, float *out_cost, float *out_info, const float *parent_cache, float *out_cache, char *err,
                int errlen) {
-    sc::Tables T;
+    sc::TablesBox T;          // (the emulation always carries the exact box narrow phase; nbox = 0 switches it off at run time)
     int rc = sc::build_tables(m, &T, err, errlen);
     if (rc) return rc;
     std::vector<float> sm(sc::WORDS_PER_TILE), tfeat((size_t)nseq * 18);

@@ -24,7 +24,7 @@
 extern "C" {
 int emu64_window(const sc_model *m, const double *parents, int E, int children, const double *actions, const double *targets,
                  int nseq, int S, int nsteps, double *out_state, double *out_cost, double *out_info, char *err, int errlen) {
-    sc::Tables T;
+    sc::TablesBox T;          // (the emulation always carries the exact box narrow phase; nbox = 0 switches it off at run time)
     int rc = sc::build_tables(m, &T, err, errlen);
     if (rc) return rc;
     std::vector<double> sm(sc::WORDS_PER_TILE), tfeat((size_t)nseq * 18);

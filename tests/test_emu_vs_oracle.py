@@ -216,11 +216,15 @@ def _box_vs_round_poses(oracle, n, seed=5):
     return np.array(out)
 
 
-def test_box_contacts_exact_narrow_phase(emu, character, oracle):
-    """Link-vs-link pairs with a box (SimParams.exact_box_contacts): a foot box against the other leg's shin capsule (box vs
-    swept segment, exact) and feet against each other (box vs box: the second as its capsule) -- the kernel's float32
+def test_box_contacts_exact_narrow_phase(emu, walk_cfg):
+    """Link-vs-link pairs with a box (SimParams.exact_box_contacts=True): a foot box against the other leg's shin capsule (box
+    vs swept segment, exact) and feet against each other (box vs box: the second as its capsule) -- the kernel's float32
     safeguarded Newton against the oracle's float64 one."""
     from helpers import legs_crossed
+    from oracle.oracle import Oracle
+    from samcon_b200.model import Character, SimParams
+    character = Character.from_config(walk_cfg, SimParams(exact_box_contacts=True))
+    oracle = Oracle(character)
     rng = np.random.default_rng(13)
     parents = np.concatenate([_box_vs_round_poses(oracle, 6), np.array([legs_crossed(rng, 0.10 + 0.02 * i, 2.0, 0.05) for i in range(2)])])
     # PD targets = the poses themselves, slightly perturbed: the touching links keep pressing / sliding on each other
@@ -241,10 +245,7 @@ def test_box_contacts_exact_narrow_phase(emu, character, oracle):
     print("box contact windows: joint rms", rms)
     assert rms.max() < 1e-3
     np.testing.assert_allclose(cost, ocost, rtol=1e-3)
-    # the capsule stand-in of round 1 is a different model: the switch changes these windows
-    from oracle.oracle import Oracle
-    from samcon_b200.config import Config
-    from samcon_b200.model import Character, SimParams
-    o1 = Oracle(Character.from_config(Config("walk"), SimParams(exact_box_contacts=False)))
+    # the capsule stand-in (the default) is a different model: the switch changes these windows
+    o1 = Oracle(Character.from_config(walk_cfg, SimParams(exact_box_contacts=False)))
     ost1, _, _ = o1.window(parents, actions, target, 100)
     assert joint_rms(ost1, ost).max() > 1e-3

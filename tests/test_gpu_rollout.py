@@ -132,9 +132,7 @@ def test_self_contact_window(pool, oracle):
     from helpers import legs_crossed
     rng = np.random.default_rng(7)
     n = 24
-    # (up to 0.1 rad: beyond that the feet's boxes pass through each other's cores, where the nearest-face choice of any
-    # penetration-depth rule flips on rounding)
-    parents = np.array([legs_crossed(rng, 0.03 + 0.003 * i, 2.0 if i % 2 else 0.995, 0.1) for i in range(n)])
+    parents = np.array([legs_crossed(rng, 0.03 + 0.004 * i, 2.0 if i % 2 else 0.995, 0.1) for i in range(n)])
     actions = np.array([legs_crossed(rng, 0.3 + 0.008 * i)[7:75] for i in range(n)])
     target = stand(rng)
     n_self = sum((oracle.contacts_full(oracle.step(p, a, 60))[:, 1] >= 0).sum() for p, a in zip(parents[:8], actions[:8]))
@@ -300,11 +298,17 @@ def test_two_handles_and_a_side_stream(character, pool, oracle):
         other.close()
 
 
-def test_box_contacts_exact_narrow_phase(pool, oracle):
-    """Link-vs-link pairs with a box on the GPU (exact box vs swept-segment narrow phase; of two boxes the second as its
-    capsule): a foot box against the other shin, feet against each other."""
+def test_box_contacts_exact_narrow_phase(walk_cfg):
+    """Link-vs-link pairs with a box on the GPU, SimParams(exact_box_contacts=True): exact box vs swept-segment narrow phase
+    (of two boxes the second as its capsule): a foot box against the other shin, feet against each other."""
     from helpers import legs_crossed
+    from oracle.oracle import Oracle
+    from samcon_b200.model import Character, SimParams
+    from samcon_b200.pool import GpuSamplePool
     from test_emu_vs_oracle import _box_vs_round_poses
+    ch = Character.from_config(walk_cfg, SimParams(exact_box_contacts=True))
+    oracle = Oracle(ch)
+    pool = GpuSamplePool(ch, 0)
     rng = np.random.default_rng(13)
     parents = np.concatenate([_box_vs_round_poses(oracle, 12), np.array([legs_crossed(rng, 0.10 + 0.01 * i, 2.0, 0.05) for i in range(4)])])
     actions = np.array([near_action(p, rng, 0.05) for p in parents])
@@ -312,6 +316,7 @@ def test_box_contacts_exact_narrow_phase(pool, oracle):
     st, cost, info = _run(pool, parents, actions, target, 100, 1)
     ost, ocost, oinfo = oracle.window(parents, actions, target, 100)
     rms = joint_rms(st, ost)
+    pool.close()
     print(f"box contact windows: joint rms median {np.median(rms):.2e} max {rms.max():.2e}")
     assert rms.max() < JOINT_TOL
     np.testing.assert_allclose(cost, ocost, rtol=COST_RTOL)

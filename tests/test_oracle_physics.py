@@ -278,7 +278,7 @@ def test_box_segment_closest_points_against_brute_force():
 
 
 def test_exact_box_contacts_switch(walk_cfg):
-    """exact_box_contacts: feet interpenetrating sideways (box-box: the first box exact, the second its capsule) and an arm
+    """exact_box_contacts (off by default): feet interpenetrating sideways (box-box: the first box exact, the second its capsule) and an arm
     box against the torso spheres give contacts whose points lie on the box surface; the capsule stand-in of round 1 is
     still there behind the switch."""
     from helpers import legs_crossed

@@ -15,7 +15,8 @@ from samcon_b200.pool import GpuSamplePool
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 cfg = Config("walk")
-ch = Character.from_config(cfg, SimParams(self_collision=os.environ.get("SC_SELF", "1") == "1"))
+ch = Character.from_config(cfg, SimParams(self_collision=os.environ.get("SC_SELF", "1") == "1",
+                                           exact_box_contacts=os.environ.get("SC_EXACT_BOX", "0") == "1"))
 pool = GpuSamplePool(ch, 0)
 _, _, targets = bench.workload_inputs(W + 1)
 d_targets = torch.tensor(targets, dtype=torch.float32, device="cuda")
