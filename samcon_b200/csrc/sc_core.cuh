@@ -654,7 +654,7 @@ SC_DEV float box_segment(V3 h, V3 p0, V3 p1, V3 &q, V3 &p, int &axis, float &sgn
     const float dd = dot(d, d);
     float t = dd > 1e-18f ? clamp01(-dot(p0, d) / dd) : 0.0f, lo = 0.0f, hi = 1.0f;
     bool lo_seen = false, hi_seen = false;
-    for (int it = 0; it < 8; it++) {
+    for (int it = 0; it < 20; it++) {
         const V3 x = p0 + t * d;
         const V3 o = mk(x.x - fmaxf(-h.x, fminf(h.x, x.x)), x.y - fmaxf(-h.y, fminf(h.y, x.y)), x.z - fmaxf(-h.z, fminf(h.z, x.z)));
         const float g1 = dot(o, d);
@@ -665,7 +665,7 @@ SC_DEV float box_segment(V3 h, V3 p0, V3 p1, V3 &q, V3 &p, int &axis, float &sgn
         float tn = t - g1 / g2;
         if (tn <= lo) tn = lo_seen ? 0.5f * (lo + hi) : lo;
         else if (tn >= hi) tn = hi_seen ? 0.5f * (lo + hi) : hi;
-        if (fabsf(tn - t) < 1e-6f) { t = tn; break; }
+        if (tn == t) break;
         t = tn;
     }
     p = p0 + t * d;
