@@ -13,7 +13,7 @@ are chained exactly like the reference's solve, /root/reference/samcon/core/samc
   sweep     #4: 10^6 rollouts per window IN TOTAL, split over the GPUs (strong scaling)
   cartwheel #3: cartwheel.yml (hand/foot ground contact), 10 000 / 1 000 per GPU, sharded like `walk`
   multiseq  #5: 64 synthetic sequences x walk.yml's own 2 000 / 200 solved concurrently, sequences dealt to the GPUs (no collective)
-All on synthetic SMPL-shaped reference motion (the planted-foot gait / the synthetic cartwheel; no AMASS data ships).
+All on synthetic SMPL-shaped reference motion (the planted-foot gait / the fold-to-the-hands motion; no AMASS data ships).
 
 value  = sample-sim-steps/s, whole job, everything resident in HBM (actions drawn on the device).
 e2e    = same metric through the host-facing API: per step the (S,68) actions come from pinned host memory and (state, cost,
@@ -46,7 +46,7 @@ CONFIGS = {
     # name: (cfg, motion kind, samples per GPU (None: total / N), total samples (None: per GPU x N), scaling, BASELINE config)
     "walk": ("walk", "gait", 10000, None, "weak", 2),
     "sweep": ("walk", "gait", None, 1000000, "strong", 4),
-    "cartwheel": ("cartwheel", "cartwheel", 10000, None, "weak", 3),
+    "cartwheel": ("cartwheel", "touchdown", 10000, None, "weak", 3),
     "multiseq": ("walk", "gait", None, None, "strong", 5),
 }
 WORKLOAD = {
@@ -54,8 +54,9 @@ WORKLOAD = {
             "2 sub-steps, 10 solver iters, warm-started contacts), chained windows of the synthetic SMPL-shaped planted-foot gait",
     "sweep": "throughput sweep (BASELINE config #4): 10^6 rollouts x 0.1 s window in total, split over the GPUs, walk.yml settings, "
              "chained windows of the synthetic planted-foot gait",
-    "cartwheel": "cartwheel.yml SamCon solve windows (BASELINE config #3), nSample 10k / nSave 1k per GPU sharded with the per-window "
-                 "elite exchange, chained windows of the synthetic cartwheel",
+    "cartwheel": "cartwheel.yml SamCon solve windows (BASELINE config #3: contact-rich, hand and foot ground contact), nSample 10k / "
+                 "nSave 1k per GPU sharded with the per-window elite exchange, chained windows of the synthetic fold-to-the-hands "
+                 "motion (the kinematic cartwheel cannot be followed by any search)",
     "multiseq": "multi-sequence batching (BASELINE config #5): 64 synthetic gait sequences x nSample 2000 / nSave 200 solved "
                 "concurrently, sequences dealt to the GPUs, one launch per window per GPU",
 }

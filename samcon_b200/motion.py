@@ -148,8 +148,9 @@ def _qaxis(axis, a):
     return np.concatenate([math.sin(0.5 * a) * axis / np.linalg.norm(axis), [math.cos(0.5 * a)]])
 
 
-def _lowest_point(links, pose):
-    """Height of the lowest collision point of the character for one (75,) pose with root z = 0."""
+def _lowest_point(links, pose, only=None):
+    """Height of the lowest collision point of the character (or of the links named in `only`) for one (75,) pose with
+    root z = 0."""
     from .urdf import BOX, CAPSULE, J_SPHERICAL
     from scipy.spatial.transform import Rotation as sRot
     R = [None] * len(links)
@@ -166,7 +167,7 @@ def _lowest_point(links, pose):
                 j += 1
             R[i] = R[l.parent] @ Rj
             p[i] = p[l.parent] + R[l.parent] @ l.jorg
-        for s in l.shapes:
+        for s in (l.shapes if only is None or l.name in only else ()):
             c = p[i] + R[i] @ s.pos
             Rs = R[i] @ s.rot
             if s.kind == BOX:
@@ -193,6 +194,8 @@ def make_synthetic_motion(kind="walk", T=91, fr=30, seed=0, links=None, name=Non
     """
     if kind == "gait":
         return make_gait_motion(T=T, fr=fr, seed=seed, links=links, name=name)
+    if kind == "touchdown":
+        return make_touchdown_motion(T=T, fr=fr, seed=seed, links=links, name=name)
     if links is None:
         from .urdf import load_links
         links = load_links(None)
@@ -389,3 +392,100 @@ def make_gait_motion(T=91, fr=30, seed=0, links=None, name=None, step_time=0.6, 
             if np.dot(a, b) < 0:
                 pose[fidx, 3 + 4 * k:7 + 4 * k] = -b
     return {name: {"fr": fr, "pose": pose}}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# "touchdown": a contact-rich motion a physical character can follow -- stand, fold forward until both hands rest on
+# the ground in front of the planted feet (hand AND foot ground contact, what cartwheel.yml's cost weights and noise
+# table are made for), hold, stand up again.  The kinematic cartwheel above rotates the whole body like a rigid wheel
+# from a standing start; no search follows it (200 000 samples per window end up lying on the ground by window 15,
+# tools/cartwheel_probe.py), so solves and bench.py's config 3 run on this motion and the cartwheel stays what it is good
+# for: a source of hand-stand states for the parity tests.
+# ----------------------------------------------------------------------------------------------------------
+def make_touchdown_motion(T=100, fr=30, seed=0, links=None, name=None, fold_time=1.2, hold_time=0.6, start=0.4,
+                          half_width=0.10, hips_back=0.85, shin=0.05, spine=0.2, hand_clearance=-0.005):
+    """-> {name: {'fr': fr, 'pose': (T,75)}}.  Sagittal and symmetric: feet stay flat on their footholds (the root pose
+    follows from the leg chain), the pelvis pitch at full fold is chosen so that the hands' spheres press
+    `-hand_clearance` m into the ground, arms hang along the world's vertical throughout."""
+    if links is None:
+        from .urdf import load_links
+        links = load_links(None)
+    rng = np.random.default_rng(seed)
+    var = 1.0 + (0.05 * rng.standard_normal(3) if seed else np.zeros(3))
+    fold_time, hips_back, spine = fold_time * var[0], hips_back * var[1], spine * var[2]
+    name = name or f"synthetic_touchdown_{seed}"
+    idx = {l.name: i for i, l in enumerate(links)}
+    jorg = {n: links[idx[n]].jorg for n in idx}
+    sole = 0.09 + 0.001
+    up_R = _rot_x(0.5 * np.pi)
+
+    def frame(s, phi_max):
+        """joint quaternions + root pose (upright frame: x left, y up, z forward) at fold fraction s in [0, 1]"""
+        phi = phi_max * s                                    # pelvis pitch (forward)
+        psi_t = -hips_back * s                               # thigh's pitch in the world: hips go back (and down) so that the
+        a_h = psi_t - phi                                    # centre of mass stays over the feet while the torso comes forward
+        a_k = shin * s - psi_t                               # knees bend; the shins stay close to vertical
+        a_a = -(phi + a_h + a_k)                             # ankles keep the soles level
+        q = {n: np.array([0.0, 0.0, 0.0, 1.0]) for n in JOINTS}
+        for side, (hip, kn, ank) in ((1.0, ("lhip", "lknee", "lankle")), (-1.0, ("rhip", "rknee", "rankle"))):
+            q[hip], q[kn], q[ank] = _qx(a_h), _qx(a_k), _qx(a_a)
+        q["lowerback"] = _qx(spine * s)
+        q["upperback"] = _qx(spine * s)
+        beta = phi + 2 * spine * s                           # pitch of the chest: arms hang along the world's vertical
+        q["lshoulder"] = _mat_to_quat(_rot_x(-beta) @ _rot_z(-0.5 * np.pi))
+        q["rshoulder"] = _mat_to_quat(_rot_x(-beta) @ _rot_z(0.5 * np.pi))
+        # root pose from the planted left foot upwards (the right leg mirrors it)
+        R_root = _rot_x(phi)
+        R_th = R_root @ _rot_x(a_h)
+        R_sh = R_th @ _rot_x(a_k)
+        ankle = np.array([half_width, sole, 0.0])
+        knee_p = ankle - R_sh @ jorg["lankle"]
+        hip_p = knee_p - R_th @ jorg["lknee"]
+        root = hip_p - R_root @ jorg["lhip"]
+        root[0] = 0.0
+        return q, R_root, root
+
+    def lowest_hand(phi_max):
+        q, R_root, root = frame(1.0, phi_max)
+        pose = _pack_pose(q, R_root, root, up_R)
+        return _lowest_point(links, pose, only=("lwrist", "rwrist")) + pose[2]
+
+    lo, hi = 0.8, 2.4                                        # pelvis pitch at full fold: hands reach the ground
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        if lowest_hand(mid) > hand_clearance:
+            lo = mid
+        else:
+            hi = mid
+    phi_max = 0.5 * (lo + hi)
+    pose = np.zeros((T, 75))
+    for f in range(T):
+        t = f / fr
+        u = (t - start) / fold_time
+        if u <= 0:
+            s = 0.0
+        elif u < 1:
+            s = 0.5 - 0.5 * math.cos(math.pi * u)
+        elif t < start + fold_time + hold_time:
+            s = 1.0
+        else:
+            u2 = (t - start - fold_time - hold_time) / fold_time
+            s = 0.5 + 0.5 * math.cos(math.pi * min(1.0, u2))
+        q, R_root, root = frame(s, phi_max)
+        pose[f] = _pack_pose(q, R_root, root, up_R)
+    for f in range(1, T):
+        for k in range(18):
+            a, b = pose[f - 1, 3 + 4 * k:7 + 4 * k], pose[f, 3 + 4 * k:7 + 4 * k]
+            if np.dot(a, b) < 0:
+                pose[f, 3 + 4 * k:7 + 4 * k] = -b
+    return {name: {"fr": fr, "pose": pose}}
+
+
+def _pack_pose(q, R_root, root, up_R):
+    """(joint quats by name, root rotation / position in the upright frame) -> one (75,) pose row in world coordinates."""
+    pose = np.zeros(75)
+    pose[0:3] = up_R @ root
+    pose[3:7] = _mat_to_quat(up_R @ R_root)
+    for k, n in enumerate(JOINTS):
+        pose[7 + 4 * k:11 + 4 * k] = q[n]
+    return pose

@@ -34,7 +34,7 @@ if __name__ == "__main__":
         if not args.synthetic:
             print(f"{cfg.data_path} not found: solving the synthetic '{args.cfg}' motion (pass --synthetic to silence)")
         # generated long enough that the last window's target (t = nIter / fps_act) lies inside the cycle
-        motion = make_synthetic_motion("cartwheel" if "cartwheel" in args.cfg else "gait", T=3 * cfg.nIter + 10, fr=30, seed=0)
+        motion = make_synthetic_motion("touchdown" if "cartwheel" in args.cfg else "gait", T=3 * cfg.nIter + 10, fr=30, seed=0)
         (name, _), = motion.items()
         cfg.motion_seq = name
         data = AmassMotionData(motion, name)

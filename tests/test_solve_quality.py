@@ -123,3 +123,39 @@ def test_gpu_walk_solve_tracks_motion(walk_cfg, character, nSample, nSave):
     assert elite_best.max() <= 8.0
     assert dz.max() < 0.1
     assert best["cost"].max() <= 8.0
+
+
+@pytest.mark.gpu
+def test_gpu_cartwheel_cfg_solve_tracks_touchdown_motion():
+    """cartwheel.yml (its cost weights and noise table) on the contact-rich motion solves and bench config 3 use: standing ->
+    folded forward with both hands on the ground -> standing, hand AND foot ground contact.  nSample 2000 / nSave 200, 34
+    windows (the whole motion): the search keeps the character on its feet / hands (root height within 0.15 m of the
+    target) with best elite costs in the reference's plotted range for its cartwheel (elite 0.5-21), and the
+    hands do carry load in the hold.  (The kinematic cartwheel of make_synthetic_motion("cartwheel") cannot be followed by
+    any search -- 200 000 samples per window end on the ground, tools/cartwheel_probe.py -- and only serves as a source of
+    hand-stand states for the parity tests.)"""
+    from samcon_b200.batched import BatchedSamCon
+    from samcon_b200.config import Config
+    from samcon_b200.model import Character
+    from samcon_b200.motion import AmassMotionData, make_synthetic_motion
+    from samcon_b200.pool import GpuSamplePool
+    from oracle.oracle import Oracle
+    cfg = Config("cartwheel")
+    ch = Character.from_config(cfg)
+    m = make_synthetic_motion("touchdown", T=112, seed=0)
+    (name, _), = m.items()
+    pool = GpuSamplePool(ch, 0)
+    try:
+        r = BatchedSamCon(cfg, [AmassMotionData(m, name)], pool, nIter=34, nSample=2000, nSave=200).sample()[0]
+    finally:
+        pool.close()
+    dz = np.abs(r["simulated_state"][:, 2] - r["target_state"][:, 2])
+    worst = r["elite_cost"][:, 0].max()
+    o = Oracle(ch)
+    hold = r["simulated_state"][18]                                  # t = 1.9 s: folded, hands down
+    links = {int(c[0]) for c in o.contacts(hold)}
+    print(f"touchdown solve: worst best-elite cost {worst:.2f}, path cost max {r['cost'].max():.2f}, root height error max {dz.max():.3f} m, "
+          f"links on the ground in the hold: {sorted(links)}")
+    assert worst <= 21.0 and r["cost"].max() <= 21.0
+    assert dz.max() < 0.15
+    assert links & {15, 19} and links & {3, 6}                       # a hand (wrist sphere) and a foot
