@@ -17,6 +17,12 @@ import numpy as np
 import yaml
 
 _PKG_CFG = osp.join(osp.dirname(osp.abspath(__file__)), "data", "cfg")
+_SCALAR_KEYS = ("fps_sim", "fps_act", "seed", "auto_nIter", "nIter", "nSample", "nSave", "data_path", "motion_seq", "noise_type",
+                "model_file", "scale", "height", "self_collision", "joint_weights", "end_effectors", "cost_weights")
+
+
+def _column(rows, c):
+    return np.array([float(r[c]) for r in rows])
 
 
 class Config:
@@ -47,33 +53,15 @@ class Config:
             for d in (self.output_dir, self.info_dir, self.log_dir):
                 os.makedirs(d, exist_ok=True)
 
-        self.fps_sim = cfg["fps_sim"]
-        self.fps_act = cfg["fps_act"]
-        self.seed = cfg["seed"]
-        self.auto_nIter = cfg["auto_nIter"]
-        self.nIter = cfg["nIter"]
-        self.nSample = cfg["nSample"]
-        self.nSave = cfg["nSave"]
-
-        self.data_path = cfg["data_path"]
-        self.motion_seq = cfg["motion_seq"]
-
-        self.noise_type = cfg["noise_type"]
+        # cfg keys that become attributes of the same name (reference: samcon/utils/config.py:34-68)
+        for key in _SCALAR_KEYS:
+            setattr(self, key, cfg[key])
+        # per-joint tables: rows of [name, value, ...] in the yml, columns as arrays here
         if "joint_noises" in cfg:
-            self.values = np.array([float(r[1]) for r in cfg["joint_noises"]])
-
-        self.model_file = cfg["model_file"]
-        self.scale = cfg["scale"]
-        self.height = cfg["height"]
-        self.self_collision = cfg["self_collision"]
+            self.values = _column(cfg["joint_noises"], 1)                      # noise range / variance per Euler angle
         if "joint_params" in cfg:
-            self.kps = np.array([float(r[1]) for r in cfg["joint_params"]])
-            self.kds = np.array([float(r[2]) for r in cfg["joint_params"]])
-            self.max_forces = np.array([float(r[3]) for r in cfg["joint_params"]])
+            self.kps, self.kds, self.max_forces = (_column(cfg["joint_params"], c) for c in (1, 2, 3))
             self.char_info = {"kps": self.kps, "kds": self.kds, "max_forces": self.max_forces}
-        self.joint_weights = cfg["joint_weights"]
-        self.end_effectors = cfg["end_effectors"]
-        self.cost_weights = cfg["cost_weights"]
 
     def get(self, key, default=None):
         return self.cfg_dict.get(key, default)

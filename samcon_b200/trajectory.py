@@ -57,49 +57,8 @@ class Trajectory:
     def get_elite_inds(self, i):
         return np.array(self.elite_inds[i], dtype=np.int64)
 
-    # all samples (num = nSample)
-    def get_prev_uid(self, i):
-        return np.array(self.prev_uid[i], dtype=np.int64)
-
-    def get_curr_uid(self, i):
-        return np.array(self.curr_uid[i], dtype=np.int64)
-
-    def get_target_state(self, i):
-        return np.array(self.target_state[i], dtype=np.float64)
-
-    def get_simulated_state(self, i):
-        return np.array(self.simulated_state[i], dtype=np.float64)
-
-    def get_action(self, i):
-        return np.array(self.action[i], dtype=np.float64)
-
-    def get_cost(self, i):
-        return np.array(self.cost[i], dtype=np.float64)
-
-    def get_info(self, i):
-        return np.array(self.info[i], dtype=np.float64)
-
-    # elite samples (num = nSave)
-    def get_prev_uid_elite(self, i):
-        return self.get_prev_uid(i)[self.get_elite_inds(i)]
-
-    def get_curr_uid_elite(self, i):
-        return self.get_curr_uid(i)[self.get_elite_inds(i)]
-
-    def get_target_state_elite(self, i):
-        return self.get_target_state(i)[self.get_elite_inds(i)]
-
-    def get_simulated_state_elite(self, i):
-        return self.get_simulated_state(i)[self.get_elite_inds(i)]
-
-    def get_action_elite(self, i):
-        return self.get_action(i)[self.get_elite_inds(i)]
-
-    def get_cost_elite(self, i):
-        return self.get_cost(i)[self.get_elite_inds(i)]
-
-    def get_info_elite(self, i):
-        return self.get_info(i)[self.get_elite_inds(i)]
+    def _column(self, field, i, dtype):
+        return np.array(getattr(self, field)[i], dtype=dtype)
 
     def select(self, i, mode="greedy", elite_inds=None):
         """trajectory.py:108-116.  ``elite_inds`` lets the caller hand in the device top-k result (same order:
@@ -176,3 +135,22 @@ class Trajectory:
         joblib.dump(out, osp.join(cfg.output_dir, f"{cfg.id}_{time_flag}.pkl"))
         joblib.dump(info, osp.join(cfg.info_dir, f"{cfg.id}_{time_flag}.pkl"))
         return out, info
+
+
+# The reference's accessor family (trajectory.py:57-106): get_<field>(i) for all nSample samples of window i and
+# get_<field>_elite(i) for its nSave elites, generated from the field table instead of written out fourteen times.
+def _install_getters():
+    fields = {"prev_uid": np.int64, "curr_uid": np.int64, "target_state": np.float64, "simulated_state": np.float64,
+              "action": np.float64, "cost": np.float64, "info": np.float64}
+    for field, dtype in fields.items():
+        def get_all(self, i, _f=field, _d=dtype):
+            return self._column(_f, i, _d)
+
+        def get_elite(self, i, _f=field, _d=dtype):
+            return self._column(_f, i, _d)[self.get_elite_inds(i)]
+        get_all.__name__, get_elite.__name__ = f"get_{field}", f"get_{field}_elite"
+        setattr(Trajectory, get_all.__name__, get_all)
+        setattr(Trajectory, get_elite.__name__, get_elite)
+
+
+_install_getters()
