@@ -63,6 +63,21 @@ WORKLOAD = {
 MULTISEQ_Q, MULTISEQ_S, MULTISEQ_E = 64, 2000, 200
 
 
+def static_config(name, world, samples=0):
+    """The `config` object of the JSON line: what the workload is, nothing that depends on the run -- both arms print the
+    same one (the reference arm times a bounded sample of it, described in its cpu_baseline.sample)."""
+    cfgname, kind, per_gpu, total, scaling, bcfg = CONFIGS[name]
+    if name == "multiseq":
+        return {"workload": WORKLOAD[name], "baseline_config": bcfg, "sequences": MULTISEQ_Q, "nSample": MULTISEQ_S, "nSave": MULTISEQ_E,
+                "steps_per_window": STEPS_PER_WINDOW, "l2": "256 MB memset between steps (inside the timed region)",
+                "parallelism": f"sequences dealt x{world}"}
+    S = samples or (per_gpu if per_gpu else total // world)
+    S -= S % 10
+    return {"workload": WORKLOAD[name], "baseline_config": bcfg, "nSample_per_gpu": S, "nSave_per_gpu": S // 10,
+            "steps_per_window": STEPS_PER_WINDOW, "l2": "256 MB memset between steps (inside the timed region)",
+            "parallelism": f"samples sharded x{world}"}
+
+
 def workload_inputs(n_windows, cfgname="walk", kind="gait", seed=0):
     from samcon_b200.config import Config
     from samcon_b200.model import Character
@@ -178,8 +193,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
             "warmup": W, "ms_per_step": 1e3 * el / K, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD[args.config], "baseline_config": CONFIGS[args.config][5],
-                       "sample_per_step": S, "best_elite_cost_last_window": float(cost[idx[0]])},
+            "config": static_config(args.config, args.gpus, args.samples),
+            "solve": {"sample_per_step": S, "best_elite_cost_last_window": float(cost[idx[0]])},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"a search of its own over the same motion, chained windows, {S} rollouts x {STEPS_PER_WINDOW} "
                                        f"steps per step on {cores} host threads; CPU restatement (oracle/samcon_oracle.c, float64), "
@@ -406,14 +421,13 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD[args.config], "baseline_config": bcfg,
-                       "nSample_per_gpu": S, "nSave_per_gpu": E, "steps_per_window": STEPS_PER_WINDOW,
-                       "l2": "256 MB memset between steps (inside the timed region)", "parallelism": f"samples sharded x{world}",
-                       "elite_exchange": search.exchange, "exchange_check": check,
-                       "best_elite_cost_last_window": best_cost, "solve_tracks_motion": bool(best_cost < 10.0),
-                       "contact_cap": {"max_contacts": 8, "frac_substeps_over_cap_in_margin": overflow / max(1, substeps),
-                                       "frac_substeps_over_cap_touching": overflow_touching / max(1, substeps)},
-                       "walk_yml_window_s_at_nSample_2000": walk_window_s},
+            "config": static_config(args.config, world, args.samples),
+            # what this run found (not part of the workload's description)
+            "solve": {"elite_exchange": search.exchange, "exchange_check": check,
+                      "best_elite_cost_last_window": best_cost, "solve_tracks_motion": bool(best_cost < 10.0),
+                      "contact_cap": {"max_contacts": 8, "frac_substeps_over_cap_in_margin": overflow / max(1, substeps),
+                                      "frac_substeps_over_cap_touching": overflow_touching / max(1, substeps)},
+                      "walk_yml_window_s_at_nSample_2000": walk_window_s},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": S * 68 * 4 + 132 * 4,
                     "d2h_bytes_per_step": S * (132 + 1 + 5) * 8 + E * world * 8},   # float64 results (widened on the device), int64 elite ids
@@ -494,9 +508,9 @@ def run_multiseq(args, world, rank, local, dev):
     value = Q * MULTISEQ_S * STEPS_PER_WINDOW * K / (ms.item() * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms.item() / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD["multiseq"], "baseline_config": 5, "sequences": Q, "sequences_per_gpu": q1 - q0,
-                       "nSample": MULTISEQ_S, "nSave": MULTISEQ_E, "l2": "256 MB memset between steps", "parallelism": f"sequences dealt x{world}",
-                       "sequence_windows_per_s": Q * K / (ms.item() * 1e-3), "worst_best_elite_cost_last_window": worst.item()},
+            "config": static_config("multiseq", world),
+            "solve": {"sequences_per_gpu": q1 - q0, "sequence_windows_per_s": Q * K / (ms.item() * 1e-3),
+                      "worst_best_elite_cost_last_window": worst.item()},
             "clocks": clk.summary(), "gpu_launches": int(pool.launch_count - l0)}
     if rank == 0:
         print(json.dumps(line))
