@@ -179,3 +179,73 @@ def solve_sequences_sharded(cfg, data_loaders, pool, rank: int, world: int, **kw
     if q1 <= q0:
         return q0, []
     return q0, BatchedSamCon(cfg, data_loaders[q0:q1], pool, seed_offset=q0, **kw).sample()
+
+
+class ShardedSamCon:
+    """A whole SamCon solve of ONE sequence with the window's samples sharded over the ranks (BASELINE config 3: "solve
+    sharded over 8 GPUs"): the reference's loop (/root/reference/samcon/core/samcon.py:144-198) with ``ShardedSearch.window``
+    in the place of the worker pool.  Every rank draws the perturbations of its own samples on the device (Philox stream
+    cfg.seed + 1000 * rank, window t); per window rank 0 additionally receives the E elites' (state, action) rows -- one
+    reduce of a zero-padded [E, 200] buffer, outside the selection's critical path -- and keeps the history the best-path
+    back-trace needs.  ``sample()`` returns, on rank 0, the per-path arrays of the reference's result dict for the best path
+    (``simulated_state``, ``action``, ``cost``, ``target_state``, ``t0_state``, ``total_cost``) plus ``elite_cost``; None on the
+    other ranks."""
+
+    def __init__(self, cfg, data_loader, pool, rank, world, nIter=None, nSample=None, nSave=None, group=None):
+        self.cfg, self.loader, self.pool, self.rank, self.world, self.group = cfg, data_loader, pool, rank, world, group
+        self.nIter = cfg.nIter if nIter is None else nIter
+        self.S = cfg.nSample if nSample is None else nSample          # nSample of the whole search
+        self.E = cfg.nSave if nSave is None else nSave
+        if self.S % self.E != 0:
+            raise Exception("nSample should be a multiples of nSave")          # samcon.py:66-67
+        if self.S % world or self.E % world:
+            raise ValueError("nSample and nSave must split evenly over the ranks")
+        if cfg.fps_sim % cfg.fps_act != 0:
+            raise Exception("FPS_SIM should be a multiples of FPS_ACT")
+        self.steps = cfg.fps_sim // cfg.fps_act
+        self.search = ShardedSearch(pool, self.S // world, self.E, rank, world, group)
+
+    def sample(self):
+        import numpy as np
+        pool, search, dev = self.pool, self.search, getattr(self.pool, "device", torch.device("cpu"))
+        dt = 1.0 / self.cfg.fps_act
+        targets = np.stack([self.loader.getSpecTimeState(t * dt) for t in range(self.nIter + 1)])
+        d_targets = torch.tensor(targets, dtype=torch.float32, device=dev)
+        limits = torch.tensor(np.asarray(self.cfg.values), dtype=torch.float32, device=dev)
+        parents = d_targets[0:1].repeat(search.E_loc, 1).contiguous()
+        pcache = None
+        children = self.S // self.E
+        hist = []
+        for t in range(1, self.nIter + 1):
+            act = pool.sample_gen(d_targets[t], limits, search.S_loc, gaussian=self.cfg.noise_type == "gaussian",
+                                  seed=self.cfg.seed + 1000 * self.rank, window=t)
+            st, cache = search.result_buffers()
+            cost = torch.empty((search.S_loc,), dtype=torch.float32, device=dev)
+            info = torch.empty((search.S_loc, 5), dtype=torch.float32, device=dev)
+            pool.window(parents, act, d_targets[t], self.steps, out=(st, cost, info), parent_cache=pcache, out_cache=cache)
+            win_rank, win_local, gcost, gid = search.select_global(cost)
+            parents, pcache = search.fetch_block(win_rank, win_local, st, cache)
+            search._win += 1
+            # the elites' rows for the record: every rank fills in the ones it simulated, rank 0 receives the sum
+            mine = win_rank == self.rank
+            safe = torch.where(mine, win_local, torch.zeros_like(win_local)).to(torch.int32)
+            rows = torch.cat([pool.gather_rows(st, safe), pool.gather_rows(act, safe)], dim=1)
+            rows = torch.where(mine[:, None], rows, torch.zeros((), dtype=torch.float32, device=dev)).contiguous()
+            if self.world > 1:
+                dist.reduce(rows, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+            if self.rank == 0:
+                hist.append((rows[:, :STATE_DIM].cpu().numpy().astype(np.float64), rows[:, STATE_DIM:].cpu().numpy().astype(np.float64),
+                             gcost.cpu().numpy().astype(np.float64), (gid // children).cpu().numpy()))
+        if self.rank != 0:
+            return None
+        # best path: back-trace every elite of the last window through the parent slots, cheapest total (trajectory.py:118-154)
+        n, E = len(hist), self.E
+        slots = np.zeros((n, E), dtype=np.int64)
+        slots[-1] = np.arange(E)
+        for t in range(n - 1, 0, -1):
+            slots[t - 1] = hist[t][3][slots[t]]
+        total = sum(hist[t][2][slots[t]] for t in range(n))
+        j = int(np.argsort(total, kind="stable")[0])
+        pick = lambda k: np.array([hist[t][k][slots[t, j]] for t in range(n)])
+        return {"simulated_state": pick(0), "action": pick(1), "cost": pick(2), "target_state": targets[1:], "t0_state": targets[0],
+                "total_cost": float(total[j]), "elite_cost": np.stack([h[2] for h in hist]), "path_total_costs": total}

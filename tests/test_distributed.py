@@ -131,3 +131,51 @@ def test_sequences_sharded_over_ranks():
     for (c, a), (c1, a1) in zip(both, one[0][1]):
         assert c == c1
         np.testing.assert_array_equal(a, a1)
+
+
+def _solve_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from samcon_b200.config import Config
+        from samcon_b200.distributed import ShardedSamCon
+        from samcon_b200.motion import AmassMotionData, make_synthetic_motion
+        m = make_synthetic_motion("gait", T=12, seed=0)
+        (name, _), = m.items()
+        res = ShardedSamCon(Config("walk"), AmassMotionData(m, name), _make_pool(), rank, world, nIter=3, nSample=12, nSave=4).sample()
+        out[rank] = None if res is None else {k: res[k] for k in ("simulated_state", "action", "cost", "total_cost", "elite_cost", "path_total_costs")}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_solve_best_path():
+    """ShardedSamCon on 2 ranks: rank 0 gets a best path that is a chain (each window's state is the result of the stored
+    action from the previous window's state, contact cache included), its total is the cheapest of the back-traced totals,
+    and the other rank returns nothing."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_solve_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[1] is None
+    r = out[0]
+    assert r["simulated_state"].shape == (3, 132) and r["action"].shape == (3, 68) and r["elite_cost"].shape == (3, 4)
+    assert (np.diff(r["elite_cost"], axis=1) >= 0).all()
+    assert r["total_cost"] == r["path_total_costs"].min() and np.isclose(r["cost"].sum(), r["total_cost"])
+    # replay the path on the oracle: window by window from the path's own previous state (float32 rows, hence the tolerance)
+    from samcon_b200.config import Config
+    from samcon_b200.motion import AmassMotionData, make_synthetic_motion
+    sys.path.insert(0, HERE)
+    from helpers import joint_rms
+    pool = _make_pool()
+    m = make_synthetic_motion("gait", T=12, seed=0)
+    (name, _), = m.items()
+    ld = AmassMotionData(m, name)
+    s, cache = ld.getSpecTimeState(0.0), None
+    for t in range(3):
+        st, c, _, cc = pool.o.window(np.asarray(s, np.float32).astype(np.float64)[None], r["action"][t][None], np.asarray(ld.getSpecTimeState(0.1 * (t + 1)), np.float32).astype(np.float64), 100,
+                                     parent_cache=cache, return_cache=True)
+        assert joint_rms(st, r["simulated_state"][t][None])[0] < 1e-5
+        assert abs(c[0] - r["cost"][t]) < 1e-4 * max(1.0, c[0])
+        s, cache = r["simulated_state"][t], cc
