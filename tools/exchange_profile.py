@@ -31,18 +31,14 @@ for w in range(1, W + 1):
     e[0].record()
     pool.window(parents, act, d_targets[w], 100, out=(st, cost, info), parent_cache=pcache, out_cache=cache)
     e[1].record()
-    lidx, lcost = pool.select(cost, search.Ec)
     e[2].record()
-    mine = torch.cat([lcost.reshape(-1), lidx.reshape(-1).view(torch.float32)]).contiguous()
-    both = torch.empty((world * 2 * search.Ec,), dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(both, mine)
+    all_cost = torch.empty((world * S,), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(all_cost, cost.contiguous())
     e[3].record()
-    both = both.view(world, 2, search.Ec)
-    all_cost = both[:, 0, :].contiguous().view(-1)
-    all_idx = both[:, 1, :].contiguous().view(torch.int32).view(-1)
     pos, gcost = pool.select(all_cost, search.E)
-    pos = pos.reshape(-1).to(torch.int64)
-    win_rank = (pos // search.Ec).to(torch.int32); win_local = all_idx[pos].contiguous()
+    pos = pos.reshape(-1)
+    win_rank = torch.div(pos, S, rounding_mode="floor").to(torch.int32)
+    win_local = (pos - win_rank * S).to(torch.int32).contiguous()
     e[4].record()
     parents, pcache = search.fetch_block(win_rank, win_local, st, cache)
     search._win += 1
@@ -54,8 +50,8 @@ m = torch.tensor(r.mean(0), device=dev)
 allm = [torch.zeros_like(m) for _ in range(world)]
 dist.all_gather(allm, m)
 if rank == 0:
-    print(f"{world} GPUs, {len(r)} windows, ms per window per rank: rollout | local select (top {search.Ec} of {S}) | all_gather (incl. waiting "
-          f"for the slowest rank) | final select ({search.E} of {world * search.Ec}) + index math | peer fetch ({E} x 592 B)")
+    print(f"{world} GPUs, {len(r)} windows, ms per window per rank: rollout | - | all_gather of the costs (incl. waiting "
+          f"for the slowest rank) | select ({search.E} of {world * S}) + index math | peer fetch ({E} x 592 B)")
     for k, a in enumerate(allm):
         print(f"rank {k}: " + " | ".join(f"{x:7.3f}" for x in a.tolist()))
     kern = torch.stack(allm)[:, 0]
