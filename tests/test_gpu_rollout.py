@@ -320,3 +320,39 @@ def test_box_contacts_exact_narrow_phase(walk_cfg):
     print(f"box contact windows: joint rms median {np.median(rms):.2e} max {rms.max():.2e}")
     assert rms.max() < JOINT_TOL
     np.testing.assert_allclose(cost, ocost, rtol=COST_RTOL)
+
+
+def test_first_principles_on_the_device(pool, character, oracle):
+    """Two checks of the CUDA path that need no oracle for their expected value.  (i) Free flight: the whole-body linear
+    momentum changes by gravity alone (first-order integrator: error O(dt)).  (ii) A humanoid standing still: the normal
+    impulses the contact solve ends a sub-step with -- read from the contact cache -- carry the weight, sum = m g h."""
+    import torch
+    rng = np.random.default_rng(31)
+    # (i)
+    s0 = np.array([rand_state(rng, 1.0, 5.0) for _ in range(4)])
+    acts = s0[:, 7:75].copy()
+    d = torch.tensor(s0, dtype=torch.float32, device="cuda")
+    f0 = pool.cost(d, d).cpu().numpy()                    # warm-up of the cost path; features are read through the oracle below
+    pool.step(d, acts.astype(np.float32), 200)
+    s1 = d.cpu().numpy().astype(np.float64)
+    for a, b in zip(s0, s1):
+        _, _, _, v0 = oracle.link_coms(a)
+        _, _, _, v1 = oracle.link_coms(b)
+        np.testing.assert_allclose(v1 - v0, [0.0, 0.0, -9.8 * 0.2], atol=0.06)      # PD torques are internal forces
+    del f0
+    # (ii)
+    s = stand(rng, 0.0, 0.0, 0.99)
+    s[0:2] = 0
+    st = torch.tensor(s[None], dtype=torch.float32, device="cuda")
+    cache = pool.empty_cache(1)
+    act = s[None, 7:75].astype(np.float32)
+    pool.step(st, act, 400, cache=cache)
+    sums = []
+    for _ in range(50):
+        pool.step(st, act, 1, cache=cache)
+        c = cache.cpu().numpy()[0]
+        assert (c[:8] >= 0).sum() >= 4                    # both feet on the ground
+        sums.append(c[8:].sum())
+    h = character.sim.dt / character.sim.num_substeps
+    weight = sum(l.mass for l in character.links) * 9.8
+    assert abs(np.mean(sums) / h - weight) / weight < 0.01
