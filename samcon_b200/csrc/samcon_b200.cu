@@ -23,6 +23,9 @@ __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *_
         int4 *dst = reinterpret_cast<int4 *>(smem);
         for (int i = threadIdx.x; i < TABLE_WORDS / 4; i += blockDim.x) dst[i] = src[i];
     }
+    // behind the tiles: the bookkeeping of the CTA's shared contact assembly (sc_core.cuh: assembly_shared), epochs start at 1
+    int *coop = reinterpret_cast<int *>(smem + TABLE_WORDS + (blockDim.x >> 5) * WORDS_PER_TILE);
+    for (int i = threadIdx.x; i < COOP_WORDS; i += blockDim.x) coop[i] = 0;
     __syncthreads();
     const TT &T = *reinterpret_cast<const TT *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *_
     for (int r = 0; r < rounds; r++) {
         const int t = r * wpr + warp;
         const bool active = warp < wpr && t < mine;
-        rollout_tile(sm, T, a, active ? (first + t) * TILE : a.S, lane, lane + 1 SC_PROF_PASS);
+        rollout_tile(sm, T, a, active ? (first + t) * TILE : a.S, lane, lane + 1, coop, r * a.nsteps * T.nsub SC_PROF_PASS);
     }
 #if defined(SC_PROFILE)
     if (lane == 0 && a.prof)
@@ -480,7 +483,7 @@ extern "C" int sc_create(sc_handle *out, const sc_model *model, int device) {
     SC_CUDA(h, cudaMalloc(&h->d_tables, TABLE_WORDS * 4));
     SC_CUDA(h, cudaMemset(h->d_tables, 0, TABLE_WORDS * 4));
     SC_CUDA(h, cudaMemcpy(h->d_tables, &h->h_tables, sizeof(Tables), cudaMemcpyHostToDevice));
-    h->smem_bytes = (TABLE_WORDS + WPB * WORDS_PER_TILE) * 4;
+    h->smem_bytes = (TABLE_WORDS + WPB * WORDS_PER_TILE + COOP_WORDS) * 4;
     SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesCapsule>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesBox>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     int nsm = 0, per_sm = 0;
@@ -559,7 +562,7 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a, cudaStream_t s
     // 28.0 ms per window); walk.yml's own 2000 samples are 4 tiles per SM: 4 warps instead of 10.
     const int mine = (ntiles + grid - 1) / grid, rounds = (mine + WPB - 1) / WPB;
     const int nw = (mine + rounds - 1) / rounds, threads = 32 * nw;
-    const int smem = (TABLE_WORDS + nw * WORDS_PER_TILE) * 4;
+    const int smem = (TABLE_WORDS + nw * WORDS_PER_TILE + COOP_WORDS) * 4;
 #if defined(SC_PROFILE)
     RolloutArgs ap = a;
     if (!h->d_prof) { cudaMalloc(&h->d_prof, SC_NPHASE * sizeof(long long)); cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long)); }

@@ -41,6 +41,14 @@
 #define SC_BAR_MASK 31
 #endif
 #define SC_BAR(bit) do { if (SC_BAR_MASK & (bit)) SC_CTA_SYNC(); } while (0)
+// Contact-matrix assembly shared between the warps of a CTA (assembly_shared below): a warp that has finished its own
+// tile's columns takes column calls of the tiles that have not, instead of standing at the barrier after the assembly.
+#ifndef SC_SHARE_ASSEMBLY
+#define SC_SHARE_ASSEMBLY 1
+#endif
+#ifndef SC_POLL_NS
+#define SC_POLL_NS 100
+#endif
 #else
 #define SC_DEV static inline
 #define SC_PHASE static
@@ -1160,6 +1168,69 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
 }
 #endif
 
+// The assembly is dealt in "column calls": in call m every lane of the warp computes column asm_column(m, slot) of its
+// sample (dealing the columns of all four samples over all 32 lanes was measured 13 % slower: lanes of one sample share 8
+// of the 32 banks, the tile's interleave only keeps different samples apart).  Columns slot, 15 - slot, 16 + slot: a
+// column evaluates the rows at or after its own, so the calls get cheaper (8 contacts: 8, 6 and 3 contact rows).
+constexpr int ASM_CALLS = (3 * MAXC + LPS - 1) / LPS;
+SC_DEV int asm_column(int m, int slot) { return m == 1 ? 2 * LPS - 1 - slot : slot + LPS * m; }
+SC_DEV int asm_calls(int ncmax) {       // calls a tile with at most ncmax contacts per sample needs
+    int n = 0;
+    for (int m = 0; m < ASM_CALLS; m++) n += 3 * ncmax > (m == 1 ? LPS : LPS * m);
+    return n;
+}
+
+constexpr int COOP_WORDS = 48;          // per CTA, behind the tiles: the pool's bookkeeping (assembly_shared)
+#if defined(__CUDACC__) && SC_SHARE_ASSEMBLY
+// Shared assembly.  The column calls of a CTA's tiles are a common pool: every warp publishes its tile (number of calls,
+// claim counter, "ready" = the epoch of this sub-step) once the tile's contact list and right-hand sides are written,
+// works through its own calls, and then takes unclaimed calls of the other tiles until every tile of the CTA is claimed
+// out.  A column only reads its tile (inertias, contact list) and writes its own entries of the packed matrix, so who
+// computes it does not change a bit of the result; the CTA barrier that follows the assembly makes the helpers' writes
+// visible to the owner.  Measured reason: warps with link-link contacts need up to three expensive calls while most need
+// two cheap ones, and 10.7 % of all warp time was spent waiting for them at that barrier
+// (profiles/r2zz_final_phase_stalls.md).  coop: [0,16) ready epoch, [16,32) next call, [32,48) number of calls, per warp.
+template <class TT>
+__device__ __forceinline__ void assembly_shared(float *sm, const TT &T, int ncmax, int *coop_, int epoch) {
+    volatile int *coop = coop_;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) {
+        coop[32 + warp] = asm_calls(ncmax);
+        coop[16 + warp] = 0;
+        __threadfence_block();
+        coop[warp] = epoch;
+    }
+    __syncwarp();
+    unsigned pending = (1u << nw) - 1u;
+    int t = warp, idle = 0;
+    while (pending) {
+        int m = -1, exhausted = 0;
+        if (lane == 0 && coop[t] == epoch) {
+            __threadfence_block();
+            const int n = coop[32 + t];
+            if (coop[16 + t] < n) m = atomicAdd(coop_ + 16 + t, 1);
+            if (m < 0 || m >= n) { m = -1; exhausted = 1; }
+        }
+        m = __shfl_sync(0xffffffffu, m, 0);
+        exhausted = __shfl_sync(0xffffffffu, exhausted, 0);
+        if (m >= 0) {
+            float *S = sm + (t - warp) * WORDS_PER_TILE + (lane & (TILE - 1));
+            const int slot = lane / TILE, nc = f2i(F(O_NC)), c = asm_column(m, slot);
+            if (c < 3 * nc) contact_column(S, T, nc, c);
+            __syncwarp();
+            idle = 0;
+            continue;                                   // the same tile again: its next call may still be free
+        }
+        if (exhausted) pending &= ~(1u << t);
+        else if (++idle >= nw) { __nanosleep(SC_POLL_NS); idle = 0; }       // a full round over tiles that are not ready yet
+        if (pending) {                                  // next tile that is not known to be claimed out
+            const unsigned above = pending & ~((2u << t) - 1u);
+            t = __ffs(above ? above : pending) - 1;
+        }
+    }
+}
+#endif
+
 template <class TT>
 SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, const int part SC_PROF_ARGS) {
     if (part == 0) {
@@ -1191,16 +1262,14 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
     }
     SC_SYNC();
     SC_T(7);
+    }
+    if (part == 3) {
     // ---- contact-space matrix: the lanes of a sample take its columns round-robin, no barriers in between --------
     SC_STAGE {
         SC_LANE;
         const int nc = f2i(F(O_NC));
-        // (dealing the columns of all four samples over all 32 lanes was measured 13 % slower: lanes of one sample
-        // share 8 of the 32 banks, the tile's interleave only keeps different samples apart)
-        // columns slot, 15 - slot, 16 + slot: a column evaluates the rows at or after its own, so pairing an early column
-        // with a late one evens out the lanes (8 contacts: 13-14 contact rows per lane instead of 10-17)
-        for (int m = 0; m < (3 * MAXC + LPS - 1) / LPS; m++) {
-            const int c = m == 1 ? 2 * LPS - 1 - slot : slot + LPS * m;
+        for (int m = 0; m < ASM_CALLS; m++) {
+            const int c = asm_column(m, slot);
             if (c < 3 * nc) contact_column(S, T, nc, c);
         }
     }
@@ -1541,13 +1610,21 @@ struct RolloutArgs {
 };
 
 template <class TT>
-SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0, int L0, int L1 SC_PROF_ARGS) {
+SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0, int L0, int L1, int *coop, int epoch0 SC_PROF_ARGS) {
+    // coop / epoch0 (device only): the CTA's assembly pool and the number of sub-steps its earlier rounds have used it for
+    (void)coop; (void)epoch0;
     SC_T(15);
     if (tile0 >= a.S) {
-        // a warp without a tile in this round only keeps the CTA's phase barriers company
+        // a warp without a tile in this round keeps the CTA's phase barriers company and helps with the others' assembly
         for (int step = 0; step < a.nsteps; step++) {
             SC_BAR(1); SC_BAR(256);
-            for (int sub = 0; sub < T.nsub; sub++) { SC_BAR(2); SC_BAR(256); SC_BAR(4); SC_BAR(64); SC_BAR(16); SC_BAR(32); SC_BAR(8); }
+            for (int sub = 0; sub < T.nsub; sub++) {
+                SC_BAR(2); SC_BAR(256); SC_BAR(4); SC_BAR(64);
+#if defined(__CUDACC__) && SC_SHARE_ASSEMBLY
+                assembly_shared(sm, T, 0, coop, epoch0 + step * T.nsub + sub + 1);
+#endif
+                SC_BAR(16); SC_BAR(32); SC_BAR(8);
+            }
         }
         return;
     }
@@ -1588,6 +1665,12 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             SC_BAR(64);
             SC_T(26);
             if (ncmax > 0) contact_solve(sm, T, L0, L1, ncmax, 0 SC_PROF_PASS);      // O_TW is current: the ABA updated it
+#if defined(__CUDACC__) && SC_SHARE_ASSEMBLY
+            assembly_shared(sm, T, ncmax, coop, epoch0 + step * T.nsub + sub + 1);
+            SC_T(8);
+#else
+            if (ncmax > 0) contact_solve(sm, T, L0, L1, ncmax, 3 SC_PROF_PASS);
+#endif
             SC_BAR(16);
             SC_T(27);
             if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 1 SC_PROF_PASS); SC_T(9); }

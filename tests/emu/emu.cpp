@@ -17,13 +17,13 @@ int emu_window(const sc_model *m, const float *parents, int E, const int *parent
     // target features: the targets themselves pushed through the feature pass
     sc::RolloutArgs f = {};
     f.parents = targets; f.children = 1; f.S = nseq; f.nsteps = 0; f.out_feat = tfeat.data();
-    for (int t0 = 0; t0 < nseq; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, f, t0, 0, 32);
+    for (int t0 = 0; t0 < nseq; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, f, t0, 0, 32, nullptr, 0);
     sc::RolloutArgs a = {};
     a.parents = parents; a.parent_idx = parent_idx; a.children = children; a.actions = actions; a.targets = targets;
     a.tfeat = tfeat.data(); a.sample_seq = sample_seq; a.S = S; a.nsteps = nsteps;
     a.out_state = out_state; a.out_cost = out_cost; a.out_info = out_info;
     a.parent_cache = parent_cache; a.out_cache = out_cache;
-    for (int t0 = 0; t0 < S; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, a, t0, 0, 32);
+    for (int t0 = 0; t0 < S; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, a, t0, 0, 32, nullptr, 0);
     return 0;
 }
 int emu_words_per_sample() { return sc::WORDS_PER_SAMPLE; }

@@ -30,12 +30,12 @@ int emu64_window(const sc_model *m, const double *parents, int E, int children, 
     std::vector<double> sm(sc::WORDS_PER_TILE), tfeat((size_t)nseq * 18);
     sc::RolloutArgs f = {};
     f.parents = targets; f.children = 1; f.S = nseq; f.nsteps = 0; f.out_feat = tfeat.data();
-    for (int t0 = 0; t0 < nseq; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, f, t0, 0, 32);
+    for (int t0 = 0; t0 < nseq; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, f, t0, 0, 32, nullptr, 0);
     sc::RolloutArgs a = {};
     a.parents = parents; a.children = children; a.actions = actions; a.targets = targets;
     a.tfeat = tfeat.data(); a.S = S; a.nsteps = nsteps;
     a.out_state = out_state; a.out_cost = out_cost; a.out_info = out_info;
-    for (int t0 = 0; t0 < S; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, a, t0, 0, 32);
+    for (int t0 = 0; t0 < S; t0 += sc::TILE) sc::rollout_tile(sm.data(), T, a, t0, 0, 32, nullptr, 0);
     return 0;
 }
 }
