@@ -4,6 +4,7 @@
 #include <cooperative_groups.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 #include "sc_tables.h"
 
@@ -15,8 +16,11 @@ namespace cg = cooperative_groups;
 // ============================================================================================================
 constexpr int TABLE_WORDS = (sizeof(Tables) + 15) / 16 * 4;
 
+// WPB warps with a tile each (what shared memory holds) + up to HELPER_WARPS warps without one, which only take column calls
+// of the shared contact assembly (the register file has room for them: 12 warps x 32 x 168 registers)
+constexpr int HELPER_WARPS = 2;
 template <int WPB, class TT>
-__global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *__restrict__ gT, RolloutArgs a) {
+__global__ void __launch_bounds__(32 * (WPB + HELPER_WARPS), 1) sc_rollout_kernel(const Tables *__restrict__ gT, RolloutArgs a) {
     extern __shared__ __align__(16) float smem[];
     {
         const int4 *src = reinterpret_cast<const int4 *>(gT);
@@ -24,7 +28,7 @@ __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *_
         for (int i = threadIdx.x; i < TABLE_WORDS / 4; i += blockDim.x) dst[i] = src[i];
     }
     // behind the tiles: the bookkeeping of the CTA's shared contact assembly (sc_core.cuh: assembly_shared), epochs start at 1
-    int *coop = reinterpret_cast<int *>(smem + TABLE_WORDS + (blockDim.x >> 5) * WORDS_PER_TILE);
+    int *coop = reinterpret_cast<int *>(smem + TABLE_WORDS + a.tile_warps * WORDS_PER_TILE);
     for (int i = threadIdx.x; i < COOP_WORDS; i += blockDim.x) coop[i] = 0;
     __syncthreads();
     const TT &T = *reinterpret_cast<const TT *>(smem);
@@ -41,7 +45,7 @@ __global__ void __launch_bounds__(32 * WPB, 1) sc_rollout_kernel(const Tables *_
     const int mine = per + ((int)blockIdx.x < extra ? 1 : 0), first = blockIdx.x * per + min((int)blockIdx.x, extra);
     // WPB is the build's ceiling; the launch brings only as many warps as a round needs (blockDim.x / 32 = wpr of the fullest
     // CTA, see sc_launch_rollout), so no warp sits at the phase barriers without a tile round after round
-    const int nw = blockDim.x >> 5;
+    const int nw = a.tile_warps;                    // (the warps behind them are helpers: never active, no tile memory)
     const int rounds = (mine + nw - 1) / nw, wpr = rounds ? (mine + rounds - 1) / rounds : 0;
     for (int r = 0; r < rounds; r++) {
         const int t = r * wpr + warp;
@@ -552,7 +556,8 @@ static int sc_reserve(sc_context *h, T **p, size_t *cap, size_t need, cudaStream
     return SC_OK;
 }
 
-static int sc_launch_rollout(sc_context *h, const RolloutArgs &a, cudaStream_t st) {
+static int sc_launch_rollout(sc_context *h, const RolloutArgs &a_, cudaStream_t st) {
+    RolloutArgs a = a_;
     const int ntiles = (a.S + TILE - 1) / TILE;
     // all SMs even when there are few tiles (walk.yml's own nSample = 2000 is 500 tiles: 3-4 warps on each of 148 SMs
     // beat 10 warps on 50 of them); the kernel deals the tiles evenly
@@ -561,8 +566,16 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a, cudaStream_t s
     // fullest SM = 2 rounds either way, and 9 warps do them without a tenth warp idling at every phase barrier (27.5 vs
     // 28.0 ms per window); walk.yml's own 2000 samples are 4 tiles per SM: 4 warps instead of 10.
     const int mine = (ntiles + grid - 1) / grid, rounds = (mine + WPB - 1) / WPB;
-    const int nw = (mine + rounds - 1) / rounds, threads = 32 * nw;
+    const int nw = (mine + rounds - 1) / rounds;
+    // helper warps (no tile, assembly calls only) up to what the register file holds next to the tile warps; none for the
+    // launches that only evaluate features or costs
+    static const int env_helpers = getenv("SC_HELPERS") ? atoi(getenv("SC_HELPERS")) : -1;      // developer knob
+    // (measured: 4 % at walk.yml's own 2000 samples = 4 tile warps per CTA, nothing at 9-10 tile warps)
+    int nhelp = a.nsteps > 0 ? (env_helpers >= 0 ? env_helpers : (nw <= WPB / 2 ? HELPER_WARPS : 0)) : 0;
+    if (nhelp > HELPER_WARPS + WPB - nw) nhelp = HELPER_WARPS + WPB - nw;
+    const int threads = 32 * (nw + nhelp);
     const int smem = (TABLE_WORDS + nw * WORDS_PER_TILE + COOP_WORDS) * 4;
+    a.tile_warps = nw;
 #if defined(SC_PROFILE)
     RolloutArgs ap = a;
     if (!h->d_prof) { cudaMalloc(&h->d_prof, SC_NPHASE * sizeof(long long)); cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long)); }

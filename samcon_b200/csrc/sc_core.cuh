@@ -61,7 +61,7 @@
 // Optional phase timing (developer builds only: -DSC_PROFILE, tools/phase_profile.py).  SC_T(i) charges the cycles
 // since the previous mark to phase i of this warp.
 #if defined(SC_PROFILE) && defined(__CUDACC__)
-#define SC_NPHASE 32
+#define SC_NPHASE 40
 #define SC_T(i) do { long long t_ = clock64(); sc_prof_acc[i] += t_ - sc_prof_last; sc_prof_last = t_; } while (0)
 #define SC_PROF_ARGS , long long *sc_prof_acc, long long &sc_prof_last
 #define SC_PROF_PASS , sc_prof_acc, sc_prof_last
@@ -1046,6 +1046,8 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
                 const int bi = s2 ? cb_b(cbi) : cb_a(cbi);
                 if (bi < 0) break;
                 V3 aw = awc, al = alc;
+                // (remembering the responses of the last four bodies instead of one was measured: bit-identical and 5 %
+                // slower per window -- the select chains cost more than the sweeps they save)
                 if (s2 || bi != bprev) {
                     const int di = T.depth[bi];
                     aw = mk(x[0], x[1], x[2]); al = mk(x[3], x[4], x[5]);
@@ -1145,9 +1147,10 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
             // the owner's residual of this row: inside a run, the value formed from its own previous change
             const float rcur = m > 0 ? spec : res[m];
             float nl = lam[m] + rcur * dgi[m];
-            const float lim = k == 0 ? 3.0e38f : muc[c] * lamn[c];
-            nl = fminf(lim, fmaxf(k == 0 ? 0.0f : -lim, nl));
-            const float dloc = slot == owner ? nl - lam[m] : 0.0f;
+            if (k == 0) nl = fmaxf(0.0f, nl);
+            else { const float lim = muc[c] * lamn[c]; nl = fminf(lim, fmaxf(-lim, nl)); }
+            // only the owner's value is read (by the shuffle below and by its own next row): the other lanes' is never used
+            const float dloc = nl - lam[m];
             if (slot == owner) lam[m] = nl;
             if (m + 1 < RPL) spec = res[m + 1] - a[m + 1][r] * dloc;
             const float d = __shfl_sync(0xffffffffu, dloc, src0 + TILE * owner);
@@ -1180,7 +1183,7 @@ SC_DEV int asm_calls(int ncmax) {       // calls a tile with at most ncmax conta
     return n;
 }
 
-constexpr int COOP_WORDS = 48;          // per CTA, behind the tiles: the pool's bookkeeping (assembly_shared)
+constexpr int COOP_WORDS = 64;          // per CTA, behind the tiles: the pool's bookkeeping (assembly_shared)
 #if defined(__CUDACC__) && SC_SHARE_ASSEMBLY
 // Shared assembly.  The column calls of a CTA's tiles are a common pool: every warp publishes its tile (number of calls,
 // claim counter, "ready" = the epoch of this sub-step) once the tile's contact list and right-hand sides are written,
@@ -1191,9 +1194,18 @@ constexpr int COOP_WORDS = 48;          // per CTA, behind the tiles: the pool's
 // two cheap ones, and 10.7 % of all warp time was spent waiting for them at that barrier
 // (profiles/r2zz_final_phase_stalls.md).  coop: [0,16) ready epoch, [16,32) next call, [32,48) number of calls, per warp.
 template <class TT>
-__device__ __forceinline__ void assembly_shared(float *sm, const TT &T, int ncmax, int *coop_, int epoch) {
+__device__ __forceinline__ void assembly_shared(float *sm, const TT &T, int ncmax, int *coop_, int epoch SC_PROF_ARGS) {
     volatile int *coop = coop_;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#if defined(SC_PROFILE)
+    // developer build: when (cycles after the barrier in front of collide) this warp's tile is ready, its own calls are
+    // done, and it leaves the pool -- mean over the warps in [32..34], the CTA's maximum per sub-step in [35..37]
+    const bool rec = sc_prof_acc[38] >= 0;                    // [38]: cycles since that barrier at the call, < 0: a warp without a tile
+    const long long t0 = clock64() - sc_prof_acc[38];
+    int *pmax = coop_ + 48 + 4 * (epoch & 1);
+    bool own_done = !rec;
+    if (rec) { const int dt = (int)(clock64() - t0); sc_prof_acc[32] += dt; if (lane == 0) atomicMax(pmax, dt); }
+#endif
     if (lane == 0) {
         coop[32 + warp] = asm_calls(ncmax);
         coop[16 + warp] = 0;
@@ -1221,6 +1233,12 @@ __device__ __forceinline__ void assembly_shared(float *sm, const TT &T, int ncma
             idle = 0;
             continue;                                   // the same tile again: its next call may still be free
         }
+#if defined(SC_PROFILE)
+        if (t == warp && exhausted && !own_done) {
+            own_done = true;
+            const int dt = (int)(clock64() - t0); sc_prof_acc[33] += dt; if (lane == 0) atomicMax(pmax + 1, dt);
+        }
+#endif
         if (exhausted) pending &= ~(1u << t);
         else if (++idle >= nw) { __nanosleep(SC_POLL_NS); idle = 0; }       // a full round over tiles that are not ready yet
         if (pending) {                                  // next tile that is not known to be claimed out
@@ -1228,6 +1246,9 @@ __device__ __forceinline__ void assembly_shared(float *sm, const TT &T, int ncma
             t = __ffs(above ? above : pending) - 1;
         }
     }
+#if defined(SC_PROFILE)
+    if (rec) { const int dt = (int)(clock64() - t0); sc_prof_acc[34] += dt; if (lane == 0) atomicMax(pmax + 2, dt); }
+#endif
 }
 #endif
 
@@ -1607,6 +1628,7 @@ struct RolloutArgs {
     unsigned long long *stats; // [3] or null: sample-sub-steps with more candidates in the margin than max_contacts, sample-sub-steps
                                // simulated, sample-sub-steps with more TOUCHING candidates than max_contacts
     long long *prof;           // developer builds (-DSC_PROFILE): per-phase cycle counters, else null
+    int tile_warps;            // set by the launcher: warps of a CTA that own a tile (the rest only help with the assembly)
 };
 
 template <class TT>
@@ -1621,7 +1643,10 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             for (int sub = 0; sub < T.nsub; sub++) {
                 SC_BAR(2); SC_BAR(256); SC_BAR(4); SC_BAR(64);
 #if defined(__CUDACC__) && SC_SHARE_ASSEMBLY
-                assembly_shared(sm, T, 0, coop, epoch0 + step * T.nsub + sub + 1);
+#if defined(SC_PROFILE)
+                sc_prof_acc[38] = -1;
+#endif
+                assembly_shared(sm, T, 0, coop, epoch0 + step * T.nsub + sub + 1 SC_PROF_PASS);
 #endif
                 SC_BAR(16); SC_BAR(32); SC_BAR(8);
             }
@@ -1654,6 +1679,9 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             SC_T(5);
             SC_BAR(4);
             SC_T(30);
+#if defined(SC_PROFILE) && defined(__CUDACC__)
+            const long long sc_prof_t4 = clock64();
+#endif
             // positions are those of the start of the sub-step; the ABA's scratch is free for the collision pass now
             collide(sm, T, T.self, L0, L1 SC_PROF_PASS);
             contact_cache(sm, T, L0, L1);
@@ -1666,13 +1694,25 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             SC_T(26);
             if (ncmax > 0) contact_solve(sm, T, L0, L1, ncmax, 0 SC_PROF_PASS);      // O_TW is current: the ABA updated it
 #if defined(__CUDACC__) && SC_SHARE_ASSEMBLY
-            assembly_shared(sm, T, ncmax, coop, epoch0 + step * T.nsub + sub + 1);
+#if defined(SC_PROFILE)
+            sc_prof_acc[38] = clock64() - sc_prof_t4;
+#endif
+            assembly_shared(sm, T, ncmax, coop, epoch0 + step * T.nsub + sub + 1 SC_PROF_PASS);
             SC_T(8);
 #else
             if (ncmax > 0) contact_solve(sm, T, L0, L1, ncmax, 3 SC_PROF_PASS);
 #endif
             SC_BAR(16);
             SC_T(27);
+#if defined(SC_PROFILE) && defined(__CUDACC__) && SC_SHARE_ASSEMBLY
+            if ((threadIdx.x >> 5) == 0) {
+                int *pmax = coop + 48 + 4 * ((epoch0 + step * T.nsub + sub + 1) & 1);
+                for (int i = 0; i < 3; i++) sc_prof_acc[35 + i] += pmax[i];
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) { pmax[0] = 0; pmax[1] = 0; pmax[2] = 0; }
+                sc_prof_acc[39]++;
+            }
+#endif
             if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 1 SC_PROF_PASS); SC_T(9); }
             SC_BAR(32);
             SC_T(28);

@@ -26,19 +26,23 @@ rng = np.random.default_rng(0)
 args = sys.argv[1:]
 S = int(args[0]) if args and args[0].isdigit() else 10000
 modes = [a for a in args if not a.isdigit()] or ["stand", "air"]
-buf = (C.c_longlong * 32)()
+buf = (C.c_longlong * 40)()
 
 
 def report(tag, ms):
     pool._lib.sc_prof_read(pool._h, buf)
     v = np.array(list(buf), dtype=np.float64)
-    ph, st = v[:16], v[16:]
+    ph, st = v[:16], v[16:32]
     tot = ph.sum() + v[26:31].sum()
     print(f"== {tag}: {ms:.2f} ms")
     for n, x in zip(NAMES, ph):
         if x: print(f"  {n:22s} {100*x/tot:6.2f}%  {ms*x/tot:7.3f} ms")
     for n, i in (("wait before collide (after aba)", 30), ("wait after collide", 26), ("wait after assembly", 27), ("wait after gs", 28), ("wait after apply", 29)):
         if v[i]: print(f"  {n:32s} {100*v[i]/tot:6.2f}%")
+    if v[39]:
+        # shared assembly (cycles after the barrier in front of collide): mean over the warps / mean of the CTA's maximum
+        print(f"  assembly pool, cycles after the collide barrier, mean over warps | mean of the CTA maximum: tile ready {v[32]/st[0]:.0f} | {v[35]/v[39]:.0f}, "
+              f"own calls done {v[33]/st[0]:.0f} | {v[36]/v[39]:.0f}, left the pool {v[34]/st[0]:.0f} | {v[37]/v[39]:.0f}")
     if st[0]:
         # per warp-substep statistics: st[0] substeps, st[1] with contacts, st[2..6] ncmax buckets 0,1-2,3-4,5-6,7-8,
         # st[7] overflow (some sample had more candidate hits than max_contacts), st[8] sum of per-sample nc (lane 0's)
