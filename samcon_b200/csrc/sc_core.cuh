@@ -1008,7 +1008,7 @@ SC_PHASE void contact_cache(float *sm, const TT &T, int L0, int L1) {
 // base block is solved with the Cholesky factor kept from the ABA, and accelerations walk back down to the bodies
 // of the contacts i >= j; rows >= the column index land in the packed lower triangle O_AM.  A link-vs-link contact
 // is the superposition of two such single-body problems (+f on body a, -f on body b): the second pass adds.
-SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
+SC_CALL void contact_column(float *S, const Tables &T, int nc, int c, int i0) {
     const int j = c / 3, k = c - 3 * j;
     const int cbj = f2i(F(O_CB + j));
     const V3 f0 = contact_frame_of(S, j, cbj).d[k];
@@ -1038,8 +1038,12 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
         solve6(L, x);
         int bprev = -1;
         V3 awc = mk(0, 0, 0), alc = mk(0, 0, 0);
-        for (int i = j; i < nc; i++) {
+        // The walk over the contacts starts at i0 <= j, the first contact of the call's earliest column, for every lane:
+        // the lanes of a sample then walk down the tree for a new body in the same iteration (one pass of the sweep code
+        // for all of them) instead of each at its own j + t; rows before the column's own contact are not evaluated.
+        for (int i = i0; i < nc; i++) {
             const int cbi = f2i(F(O_CB + i));
+            if (i < j && (cb_b(cbi) >= 0 || cb_a(cbi) == bprev)) continue;
             V3 a = mk(0, 0, 0);
 #pragma unroll 1
             for (int s2 = 0; s2 < 2; s2++) {
@@ -1062,9 +1066,11 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c) {
                     }
                     if (!s2) { bprev = bi; awc = aw; alc = al; }
                 }
+                if (i < j) break;            // only the body's response was wanted, for the rows to come
                 const V3 ap = al + cross(aw, ld3(S, (s2 ? O_CR2 : O_CR) + 3 * i));
                 a = s2 ? a - ap : ap;
             }
+            if (i < j) continue;
             // projections on contact i's frame; a ground contact's frame is +z, -y, +x: components, no arithmetic
             V3 pr = mk(a.z, -a.y, a.x);
             if (cbi >> 8) {
@@ -1177,6 +1183,7 @@ __device__ __forceinline__ void gs_registers(float *sm, const TT &T) {
 // column evaluates the rows at or after its own, so the calls get cheaper (8 contacts: 8, 6 and 3 contact rows).
 constexpr int ASM_CALLS = (3 * MAXC + LPS - 1) / LPS;
 SC_DEV int asm_column(int m, int slot) { return m == 1 ? 2 * LPS - 1 - slot : slot + LPS * m; }
+SC_DEV int asm_first_contact(int m) { return (LPS * m) / 3; }      // contact of the call's lowest column
 SC_DEV int asm_calls(int ncmax) {       // calls a tile with at most ncmax contacts per sample needs
     int n = 0;
     for (int m = 0; m < ASM_CALLS; m++) n += 3 * ncmax > (m == 1 ? LPS : LPS * m);
@@ -1228,7 +1235,7 @@ __device__ __forceinline__ void assembly_shared(float *sm, const TT &T, int ncma
         if (m >= 0) {
             float *S = sm + (t - warp) * WORDS_PER_TILE + (lane & (TILE - 1));
             const int slot = lane / TILE, nc = f2i(F(O_NC)), c = asm_column(m, slot);
-            if (c < 3 * nc) contact_column(S, T, nc, c);
+            if (c < 3 * nc) contact_column(S, T, nc, c, asm_first_contact(m));
             __syncwarp();
             idle = 0;
             continue;                                   // the same tile again: its next call may still be free
@@ -1291,7 +1298,7 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
         const int nc = f2i(F(O_NC));
         for (int m = 0; m < ASM_CALLS; m++) {
             const int c = asm_column(m, slot);
-            if (c < 3 * nc) contact_column(S, T, nc, c);
+            if (c < 3 * nc) contact_column(S, T, nc, c, asm_first_contact(m));
         }
     }
     SC_SYNC();
