@@ -536,8 +536,8 @@ extern "C" int sc_rollout_config(sc_handle h, int *smem_bytes, int *samples_per_
 extern "C" int sc_prof_read(sc_handle h, long long *out) {
     if (!h || !h->d_prof) return SC_EINVAL;
     cudaDeviceSynchronize();
-    cudaMemcpy(out, h->d_prof, SC_NPHASE * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long));
+    cudaMemcpy(out, h->d_prof, (SC_NPHASE + SC_NTRACE) * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemset(h->d_prof, 0, (SC_NPHASE + SC_NTRACE) * sizeof(long long));
     return SC_OK;
 }
 #endif
@@ -578,7 +578,12 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a_, cudaStream_t 
     a.tile_warps = nw;
 #if defined(SC_PROFILE)
     RolloutArgs ap = a;
-    if (!h->d_prof) { cudaMalloc(&h->d_prof, SC_NPHASE * sizeof(long long)); cudaMemset(h->d_prof, 0, SC_NPHASE * sizeof(long long)); }
+    if (!h->d_prof) {
+        cudaMalloc(&h->d_prof, (SC_NPHASE + SC_NTRACE) * sizeof(long long));
+        cudaMemset(h->d_prof, 0, (SC_NPHASE + SC_NTRACE) * sizeof(long long));
+        long long *tr = h->d_prof + SC_NPHASE;
+        cudaMemcpyToSymbol(sc::sc_trace, &tr, sizeof tr);
+    }
     ap.prof = a.nsteps > 0 ? h->d_prof : nullptr;
     if (h->h_tables.self.nbox > 0) sc_rollout_kernel<WPB, TablesBox><<<grid, threads, smem, st>>>(h->d_tables, ap);
     else sc_rollout_kernel<WPB, TablesCapsule><<<grid, threads, smem, st>>>(h->d_tables, ap);

@@ -62,6 +62,8 @@
 // since the previous mark to phase i of this warp.
 #if defined(SC_PROFILE) && defined(__CUDACC__)
 #define SC_NPHASE 40
+#define SC_NTRACE 2048            // behind the counters: [0] events written, [8 + 4 k ..] event k (assembly_shared)
+namespace sc { __device__ long long *sc_trace = nullptr; }
 #define SC_T(i) do { long long t_ = clock64(); sc_prof_acc[i] += t_ - sc_prof_last; sc_prof_last = t_; } while (0)
 #define SC_PROF_ARGS , long long *sc_prof_acc, long long &sc_prof_last
 #define SC_PROF_PASS , sc_prof_acc, sc_prof_last
@@ -1235,8 +1237,24 @@ __device__ __forceinline__ void assembly_shared(float *sm, const TT &T, int ncma
         if (m >= 0) {
             float *S = sm + (t - warp) * WORDS_PER_TILE + (lane & (TILE - 1));
             const int slot = lane / TILE, nc = f2i(F(O_NC)), c = asm_column(m, slot);
+#if defined(SC_PROFILE)
+            const long long tc0 = clock64();
+#endif
             if (c < 3 * nc) contact_column(S, T, nc, c, asm_first_contact(m));
             __syncwarp();
+#if defined(SC_PROFILE)
+            if (rec) { sc_prof_acc[t == warp ? 25 : 31] += clock64() - tc0; sc_prof_acc[14] += t == warp ? 1 : 0x1000000; }
+            // trace of CTA 0: (epoch, warp, tile, call, two-body tile?, start, end) of every call of a few sub-steps
+            if (sc_trace && blockIdx.x == 0 && epoch >= 150 && epoch < 156 && lane == 0) {
+                const int k = (int)atomicAdd((unsigned long long *)sc_trace, 1ull);
+                if (k < 400) {
+                    long long *e = sc_trace + 8 + 4 * k;
+                    e[0] = epoch;
+                    e[1] = warp | t << 8 | m << 16 | (f2i(sm[(t - warp) * WORDS_PER_TILE + O_TM * TILE]) >= TM_TWO_BODY ? 1 << 24 : 0);
+                    e[2] = tc0 - t0; e[3] = clock64() - t0;
+                }
+            }
+#endif
             idle = 0;
             continue;                                   // the same tile again: its next call may still be free
         }

@@ -16,7 +16,7 @@ from samcon_b200.model import Character
 from samcon_b200.pool import GpuSamplePool
 from helpers import stand, near_action, rand_state
 NAMES = ["load", "fk", "pd_term", "aba_pd", "collide", "aba", "fk_vel", "c_rhs", "c_assembly", "c_gs", "c_apply", "integrate",
-         "features+cost+store", "cta_barrier_wait", "-", "idle/other"]
+         "features+cost+store", "cta_barrier_wait", None, "idle/other"]
 from samcon_b200.model import SimParams
 cfg = Config("walk")
 ch = Character.from_config(cfg, SimParams(self_collision=os.environ.get("SC_SELF", "1") == "1", num_solver_iters=int(os.environ.get("SC_NITER", "10"))))
@@ -26,23 +26,30 @@ rng = np.random.default_rng(0)
 args = sys.argv[1:]
 S = int(args[0]) if args and args[0].isdigit() else 10000
 modes = [a for a in args if not a.isdigit()] or ["stand", "air"]
-buf = (C.c_longlong * 40)()
+buf = (C.c_longlong * (40 + 2048))()
 
 
 def report(tag, ms):
     pool._lib.sc_prof_read(pool._h, buf)
     v = np.array(list(buf), dtype=np.float64)
     ph, st = v[:16], v[16:32]
-    tot = ph.sum() + v[26:31].sum()
+    tot = ph.sum() - ph[14] + v[26:31].sum()
     print(f"== {tag}: {ms:.2f} ms")
     for n, x in zip(NAMES, ph):
-        if x: print(f"  {n:22s} {100*x/tot:6.2f}%  {ms*x/tot:7.3f} ms")
+        if x and n: print(f"  {n:22s} {100*x/tot:6.2f}%  {ms*x/tot:7.3f} ms")
     for n, i in (("wait before collide (after aba)", 30), ("wait after collide", 26), ("wait after assembly", 27), ("wait after gs", 28), ("wait after apply", 29)):
         if v[i]: print(f"  {n:32s} {100*v[i]/tot:6.2f}%")
     if v[39]:
         # shared assembly (cycles after the barrier in front of collide): mean over the warps / mean of the CTA's maximum
         print(f"  assembly pool, cycles after the collide barrier, mean over warps | mean of the CTA maximum: tile ready {v[32]/st[0]:.0f} | {v[35]/v[39]:.0f}, "
-              f"own calls done {v[33]/st[0]:.0f} | {v[36]/v[39]:.0f}, left the pool {v[34]/st[0]:.0f} | {v[37]/v[39]:.0f}")
+              f"own calls done {v[33]/st[0]:.0f} | {v[36]/v[39]:.0f}, left the pool {v[34]/st[0]:.0f} | {v[37]/v[39]:.0f}; "
+              f"per warp-substep: {(int(v[14]) & 0xffffff) / st[0]:.2f} own calls in {v[25]/st[0]:.0f} cycles, {(int(v[14]) >> 24) / st[0]:.2f} calls of other tiles in {v[31]/st[0]:.0f} cycles")
+    ntr = int(v[40])
+    if ntr and os.environ.get("SC_TRACE"):
+        # the calls of CTA 0 in a few sub-steps: epoch, warp, tile, call, two-body tile, start and end (cycles after the collide barrier)
+        ev = sorted((int(v[48 + 4 * k]), int(v[49 + 4 * k]), int(v[50 + 4 * k]), int(v[51 + 4 * k])) for k in range(min(ntr, 400)))
+        for ep, code, t0_, t1_ in ev:
+            print(f"    epoch {ep} warp {code & 255:2d} tile {code >> 8 & 255} call {code >> 16 & 255} {'two-body' if code >> 24 else '        '} {t0_:6d} .. {t1_:6d}  ({t1_ - t0_})")
     if st[0]:
         # per warp-substep statistics: st[0] substeps, st[1] with contacts, st[2..6] ncmax buckets 0,1-2,3-4,5-6,7-8,
         # st[7] overflow (some sample had more candidate hits than max_contacts), st[8] sum of per-sample nc (lane 0's)
