@@ -356,3 +356,24 @@ def test_first_principles_on_the_device(pool, character, oracle):
     h = character.sim.dt / character.sim.num_substeps
     weight = sum(l.mass for l in character.links) * 9.8
     assert abs(np.mean(sums) / h - weight) / weight < 0.01
+
+
+def test_a_samples_result_does_not_depend_on_the_batch_around_it(pool):
+    """The CTA's warps share the contact assembly (assembly_shared): who computes a column must not change a bit.  The same
+    contact-rich samples are rolled out inside batches of different size and order -- different tiles, different numbers of
+    tile and helper warps per CTA, one or several rounds -- and every state, cost and contact cache has to be identical."""
+    from samcon_b200.config import Config
+    from samcon_b200.sampling import get_batch_action
+    rng = np.random.default_rng(11)
+    cfg = Config("walk")
+    n = 6000                                                       # 1500 tiles: 10-11 per CTA = two rounds
+    base = np.array([stand(rng, 0.04, 0.3, 0.97 + 0.0005 * (i % 40)) for i in range(64)], np.float32)
+    parents = base[rng.integers(0, 64, n)]
+    target = stand(rng, 0.03, 0.1, 0.985)
+    actions = get_batch_action(target, n, cfg.values, "uniform", np.random.RandomState(5)).astype(np.float32)
+    ref = [x.cpu().numpy() for x in pool.window(parents, actions, target.astype(np.float32), 40, children=1, out_cache=True)]
+    assert (ref[3][:, :8] >= 0).sum(1).max() >= 6                  # contact-rich: some samples hold 6+ contacts at the end
+    for pick in (np.arange(37), np.arange(n)[::-1][:1203], rng.permutation(n)[:2500]):
+        out = [x.cpu().numpy() for x in pool.window(parents[pick], actions[pick], target.astype(np.float32), 40, children=1, out_cache=True)]
+        for a, b in zip(ref, out):
+            assert np.array_equal(a[pick].view(np.uint32), b.view(np.uint32))
