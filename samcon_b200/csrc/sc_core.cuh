@@ -1043,36 +1043,35 @@ SC_CALL void contact_column(float *S, const Tables &T, int nc, int c, int i0) {
         // The walk over the contacts starts at i0 <= j, the first contact of the call's earliest column, for every lane:
         // the lanes of a sample then walk down the tree for a new body in the same iteration (one pass of the sweep code
         // for all of them) instead of each at its own j + t; rows before the column's own contact are not evaluated.
+        // walk down the tree to body bi: angular and linear acceleration of its origin
+#define SC_WALK_DOWN(bi, aw, al)                                                                                       \
+        do {                                                                                                            \
+            const int di = T.depth[bi];                                                                                 \
+            aw = mk(x[0], x[1], x[2]); al = mk(x[3], x[4], x[5]);                                                       \
+            _Pragma("unroll") for (int d = 1; d < MAXLEV; d++) {                                                        \
+                if (d <= di) {                                                                                          \
+                    const int b = T.anc[bi][d];                                                                         \
+                    al = al + cross(aw, ld3(S, O_RJ + 3 * b));                                                          \
+                    const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);                                  \
+                    aw = mul(ldS(S, O_DI + 6 * b), uu - mulT(ldM(S, O_UB + 9 * b), al));   /* K (uu - B^T al), K A = 1 */ \
+                }                                                                                                       \
+            }                                                                                                           \
+        } while (0)
         for (int i = i0; i < nc; i++) {
-            const int cbi = f2i(F(O_CB + i));
-            if (i < j && (cb_b(cbi) >= 0 || cb_a(cbi) == bprev)) continue;
-            V3 a = mk(0, 0, 0);
-#pragma unroll 1
-            for (int s2 = 0; s2 < 2; s2++) {
-                const int bi = s2 ? cb_b(cbi) : cb_a(cbi);
-                if (bi < 0) break;
-                V3 aw = awc, al = alc;
-                // (remembering the responses of the last four bodies instead of one was measured: bit-identical and 5 %
-                // slower per window -- the select chains cost more than the sweeps they save)
-                if (s2 || bi != bprev) {
-                    const int di = T.depth[bi];
-                    aw = mk(x[0], x[1], x[2]); al = mk(x[3], x[4], x[5]);
-#pragma unroll
-                    for (int d = 1; d < MAXLEV; d++) {
-                        if (d <= di) {
-                            const int b = T.anc[bi][d];
-                            al = al + cross(aw, ld3(S, O_RJ + 3 * b));
-                            const V3 uu = (d <= dj && T.anc[bj][d] == b) ? u[d] : mk(0, 0, 0);
-                            aw = mul(ldS(S, O_DI + 6 * b), uu - mulT(ldM(S, O_UB + 9 * b), al));   // aw + K (uu - A aw - B^T al), K A = 1
-                        }
-                    }
-                    if (!s2) { bprev = bi; awc = aw; alc = al; }
-                }
-                if (i < j) break;            // only the body's response was wanted, for the rows to come
-                const V3 ap = al + cross(aw, ld3(S, (s2 ? O_CR2 : O_CR) + 3 * i));
-                a = s2 ? a - ap : ap;
+            const int cbi = f2i(F(O_CB + i)), ba = cb_a(cbi), bb = cb_b(cbi);
+            if (i < j && (bb >= 0 || ba == bprev)) continue;
+            // body a's response is remembered for the contacts that follow on the same body (remembering the last four
+            // bodies instead was measured: bit-identical and 5 % slower per window -- the select chains cost more than the
+            // walks they save); the ground-contact row, nearly all of them, is straight-line code after it
+            if (ba != bprev) { SC_WALK_DOWN(ba, awc, alc); bprev = ba; }
+            if (i < j) continue;              // only the body's response was wanted, for the rows to come
+            V3 a = alc + cross(awc, ld3(S, O_CR + 3 * i));
+            if (bb >= 0) {                    // link-link: minus body b's acceleration at its contact point
+                V3 aw, al;
+                SC_WALK_DOWN(bb, aw, al);
+                a = a - (al + cross(aw, ld3(S, O_CR2 + 3 * i)));
             }
-            if (i < j) continue;
+#undef SC_WALK_DOWN
             // projections on contact i's frame; a ground contact's frame is +z, -y, +x: components, no arithmetic
             V3 pr = mk(a.z, -a.y, a.x);
             if (cbi >> 8) {
