@@ -166,6 +166,8 @@ constexpr int O_TM = O_NC + 1;                    // mask of bodies on a root pa
 constexpr int TM_TWO_BODY = 1 << 30;              // some contact of the sample is link-vs-link
 constexpr int O_RHS = O_TM + 1;                   // right-hand sides; the sweep overwrites them with the impulses:
 constexpr int O_LAM = O_RHS;                      // a lane reads the rows it owns before the sweep and writes the same rows after it
+constexpr int O_DM = O_RHS + 3 * MAXC;            // mask of the bodies that carry a contact themselves (int)
+static_assert(O_DM < O_UB, "the contact list fits into the angular-block words the dynamics pass leaves free");
 static_assert(O_RHS + NR <= O_UB + 9, "the contact list must fit in the words of O_UA");
 constexpr int O_AM = O_IC;                        // contact-space matrix, packed lower triangle (contact solve)
 constexpr int O_ZC = O_IC;                        // collide: signed distance per candidate (pairs, then ground points) ...
@@ -1294,12 +1296,14 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
             F(O_RHS + 3 * j + 2) = -dot(fr.d[2], vp);
         }
         if (slot == LPS - 1) {
-            int mask = 0;
+            int mask = 0, direct = 0;
             for (int j = 0; j < nc; j++) {
                 const int cb = f2i(F(O_CB + j));
                 mask |= T.anc_mask[cb_a(cb)] | (cb_b(cb) >= 0 ? T.anc_mask[cb_b(cb)] | TM_TWO_BODY : 0);
+                direct |= 1 << cb_a(cb) | (cb_b(cb) >= 0 ? 1 << cb_b(cb) : 0);
             }
             F(O_TM) = i2f(mask);
+            F(O_DM) = i2f(direct);
         }
 #if !defined(__CUDACC__)
         if (slot == 0) { F(O_DEL) = 0; F(O_DEL + 1) = 0; }
@@ -1411,6 +1415,8 @@ SC_PHASE void contact_solve(float *sm, const TT &T, int L0, int L1, int ncmax, c
                     const int c = T.child[b][k];
                     if ((mask >> c) & 1) { pn = pn + ld3(S, O_PC + 6 * c); pf = pf + ld3(S, O_PC + 6 * c + 3); }
                 }
+                // (only a body that carries a contact itself looks through the list: most bodies on a root path do not)
+                if ((f2i(F(O_DM)) >> b) & 1)
                 for (int j = 0; j < nc; j++) {
                     const int cb = f2i(F(O_CB + j));
                     const bool ona = cb_a(cb) == b, onb = cb_b(cb) == b;
