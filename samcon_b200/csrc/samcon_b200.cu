@@ -19,7 +19,7 @@ constexpr int TABLE_WORDS = (sizeof(Tables) + 15) / 16 * 4;
 // WPB warps with a tile each (what shared memory holds) + up to HELPER_WARPS warps without one, which only take column calls
 // of the shared contact assembly (the register file has room for them: 12 warps x 32 x 168 registers)
 constexpr int HELPER_WARPS = 2;
-template <int WPB, class TT>
+template <int WPB, class TT, int BM>
 __global__ void __launch_bounds__(32 * (WPB + HELPER_WARPS), 1) sc_rollout_kernel(const Tables *__restrict__ gT, RolloutArgs a) {
     extern __shared__ __align__(16) float smem[];
     {
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(32 * (WPB + HELPER_WARPS), 1) sc_rollout_kerne
     for (int r = 0; r < rounds; r++) {
         const int t = r * wpr + warp;
         const bool active = warp < wpr && t < mine;
-        rollout_tile(sm, T, a, active ? (first + t) * TILE : a.S, lane, lane + 1, coop, r * a.nsteps * T.nsub SC_PROF_PASS);
+        rollout_tile<TT, BM>(sm, T, a, active ? (first + t) * TILE : a.S, lane, lane + 1, coop, r * a.nsteps * T.nsub SC_PROF_PASS);
     }
 #if defined(SC_PROFILE)
     if (lane == 0 && a.prof)
@@ -488,11 +488,13 @@ extern "C" int sc_create(sc_handle *out, const sc_model *model, int device) {
     SC_CUDA(h, cudaMemset(h->d_tables, 0, TABLE_WORDS * 4));
     SC_CUDA(h, cudaMemcpy(h->d_tables, &h->h_tables, sizeof(Tables), cudaMemcpyHostToDevice));
     h->smem_bytes = (TABLE_WORDS + WPB * WORDS_PER_TILE + COOP_WORDS) * 4;
-    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesCapsule>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesBox>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesCapsule, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesBox, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesCapsule, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    SC_CUDA(h, cudaFuncSetAttribute(sc_rollout_kernel<WPB, TablesBox, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     int nsm = 0, per_sm = 0;
     SC_CUDA(h, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-    SC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc_rollout_kernel<WPB, TablesBox>, 32 * WPB, h->smem_bytes));
+    SC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc_rollout_kernel<WPB, TablesBox, 31>, 32 * WPB, h->smem_bytes));
     if (per_sm < 1) return sc_fail(h, SC_ECUDA, "rollout kernel does not fit an SM (%d B shared)", h->smem_bytes);
     h->grid_cap = nsm * per_sm;
     int sel_per_sm = 0;
@@ -576,6 +578,13 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a_, cudaStream_t 
     const int threads = 32 * (nw + nhelp);
     const int smem = (TABLE_WORDS + nw * WORDS_PER_TILE + COOP_WORDS) * 4;
     a.tile_warps = nw;
+    // Phase barriers: all five keep the warps in the same code (instruction fetch), but the one behind the shared assembly
+    // already aligns them once per sub-step, and a CTA of exactly 9 tile warps (5000 or 10 000 samples per GPU) is measured
+    // 2 % faster with only that one and the one in front of the integration (mask 24); with 4 or 10 warps all five are as
+    // good or better (interleaved A/B, profiles/r3_barrier_masks.log)
+    static const int env_mask = getenv("SC_BARRIERS") ? atoi(getenv("SC_BARRIERS")) : -1;        // developer knob: 24 or 31
+    const bool few = env_mask >= 0 ? env_mask == 24 : nw == 9;
+    const bool box = h->h_tables.self.nbox > 0;
 #if defined(SC_PROFILE)
     RolloutArgs ap = a;
     if (!h->d_prof) {
@@ -585,12 +594,14 @@ static int sc_launch_rollout(sc_context *h, const RolloutArgs &a_, cudaStream_t 
         cudaMemcpyToSymbol(sc::sc_trace, &tr, sizeof tr);
     }
     ap.prof = a.nsteps > 0 ? h->d_prof : nullptr;
-    if (h->h_tables.self.nbox > 0) sc_rollout_kernel<WPB, TablesBox><<<grid, threads, smem, st>>>(h->d_tables, ap);
-    else sc_rollout_kernel<WPB, TablesCapsule><<<grid, threads, smem, st>>>(h->d_tables, ap);
+    const RolloutArgs &al = ap;
 #else
-    if (h->h_tables.self.nbox > 0) sc_rollout_kernel<WPB, TablesBox><<<grid, threads, smem, st>>>(h->d_tables, a);
-    else sc_rollout_kernel<WPB, TablesCapsule><<<grid, threads, smem, st>>>(h->d_tables, a);
+    const RolloutArgs &al = a;
 #endif
+    if (box && few) sc_rollout_kernel<WPB, TablesBox, 24><<<grid, threads, smem, st>>>(h->d_tables, al);
+    else if (box) sc_rollout_kernel<WPB, TablesBox, 31><<<grid, threads, smem, st>>>(h->d_tables, al);
+    else if (few) sc_rollout_kernel<WPB, TablesCapsule, 24><<<grid, threads, smem, st>>>(h->d_tables, al);
+    else sc_rollout_kernel<WPB, TablesCapsule, 31><<<grid, threads, smem, st>>>(h->d_tables, al);
     h->launches++;
     SC_CUDA(h, cudaGetLastError());
     return SC_OK;

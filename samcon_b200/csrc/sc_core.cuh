@@ -41,6 +41,10 @@
 #define SC_BAR_MASK 31
 #endif
 #define SC_BAR(bit) do { if (SC_BAR_MASK & (bit)) SC_CTA_SYNC(); } while (0)
+// the step loop's barriers are also switched per kernel instance (template parameter BM of rollout_tile; a run-time mask
+// loses what dropping a barrier gains -- the compiler schedules across a barrier that is not there): which ones pay
+// depends on how many warps the CTA carries.  Bit 16, behind the shared assembly, is the only one needed for correctness.
+#define SC_BARL(bit) do { if ((SC_BAR_MASK & (bit)) && ((BM | 16) & (bit))) SC_CTA_SYNC(); } while (0)
 // Contact-matrix assembly shared between the warps of a CTA (assembly_shared below): a warp that has finished its own
 // tile's columns takes column calls of the tiles that have not, instead of standing at the barrier after the assembly.
 #ifndef SC_SHARE_ASSEMBLY
@@ -56,6 +60,7 @@
 #define SC_SYNC() ((void)0)
 #define SC_CTA_SYNC() ((void)0)
 #define SC_BAR(bit) ((void)0)
+#define SC_BARL(bit) ((void)0)
 #endif
 
 // Optional phase timing (developer builds only: -DSC_PROFILE, tools/phase_profile.py).  SC_T(i) charges the cycles
@@ -1661,7 +1666,7 @@ struct RolloutArgs {
     int tile_warps;            // set by the launcher: warps of a CTA that own a tile (the rest only help with the assembly)
 };
 
-template <class TT>
+template <class TT, int BM = 31>
 SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0, int L0, int L1, int *coop, int epoch0 SC_PROF_ARGS) {
     // coop / epoch0 (device only): the CTA's assembly pool and the number of sub-steps its earlier rounds have used it for
     (void)coop; (void)epoch0;
@@ -1669,16 +1674,16 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
     if (tile0 >= a.S) {
         // a warp without a tile in this round keeps the CTA's phase barriers company and helps with the others' assembly
         for (int step = 0; step < a.nsteps; step++) {
-            SC_BAR(1); SC_BAR(256);
+            SC_BARL(1); SC_BAR(256);
             for (int sub = 0; sub < T.nsub; sub++) {
-                SC_BAR(2); SC_BAR(256); SC_BAR(4); SC_BAR(64);
+                SC_BARL(2); SC_BAR(256); SC_BARL(4); SC_BARL(64);
 #if defined(__CUDACC__) && SC_SHARE_ASSEMBLY
 #if defined(SC_PROFILE)
                 sc_prof_acc[38] = -1;
 #endif
                 assembly_shared(sm, T, 0, coop, epoch0 + step * T.nsub + sub + 1 SC_PROF_PASS);
 #endif
-                SC_BAR(16); SC_BAR(32); SC_BAR(8);
+                SC_BARL(16); SC_BARL(32); SC_BARL(8);
             }
         }
         return;
@@ -1686,7 +1691,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
     load_state(sm, T, L0, L1, a.parents, a.parent_cache, a.parent_idx, a.children, tile0, a.S);
     SC_T(0);
     for (int step = 0; step < a.nsteps; step++) {
-        SC_BAR(1);
+        SC_BARL(1);
         SC_T(13);
         fk_sweep(sm, T, L0, L1, true);
         SC_T(1);
@@ -1702,12 +1707,12 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
         aba(sm, T, L0, L1, true);
         SC_T(3);
         for (int sub = 0; sub < T.nsub; sub++) {
-            SC_BAR(2);
+            SC_BARL(2);
             SC_T(13);
             if (sub) { fk_sweep(sm, T, L0, L1, true); SC_T(1); }
             aba(sm, T, L0, L1, false);
             SC_T(5);
-            SC_BAR(4);
+            SC_BARL(4);
             SC_T(30);
 #if defined(SC_PROFILE) && defined(__CUDACC__)
             const long long sc_prof_t4 = clock64();
@@ -1720,7 +1725,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
 #if defined(SC_PROFILE) && defined(__CUDACC__)
             sc_prof_acc[16]++; sc_prof_acc[17] += ncmax > 0; sc_prof_acc[18 + (ncmax + 1) / 2]++;
 #endif
-            SC_BAR(64);
+            SC_BARL(64);
             SC_T(26);
             if (ncmax > 0) contact_solve(sm, T, L0, L1, ncmax, 0 SC_PROF_PASS);      // O_TW is current: the ABA updated it
 #if defined(__CUDACC__) && SC_SHARE_ASSEMBLY
@@ -1732,7 +1737,7 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
 #else
             if (ncmax > 0) contact_solve(sm, T, L0, L1, ncmax, 3 SC_PROF_PASS);
 #endif
-            SC_BAR(16);
+            SC_BARL(16);
             SC_T(27);
 #if defined(SC_PROFILE) && defined(__CUDACC__) && SC_SHARE_ASSEMBLY
             if ((threadIdx.x >> 5) == 0) {
@@ -1744,10 +1749,10 @@ SC_DEV void rollout_tile(float *sm, const TT &T, const RolloutArgs &a, int tile0
             }
 #endif
             if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 1 SC_PROF_PASS); SC_T(9); }
-            SC_BAR(32);
+            SC_BARL(32);
             SC_T(28);
             if (ncmax > 0) { contact_solve(sm, T, L0, L1, ncmax, 2 SC_PROF_PASS); SC_T(10); }
-            SC_BAR(8);
+            SC_BARL(8);
             SC_T(29);
             integrate(sm, T, L0, L1);
             SC_T(11);
