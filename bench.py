@@ -208,7 +208,13 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 def rollout_traffic():
     """DRAM bytes of one rollout launch from this round's committed ncu capture (tools/ncu_summary.py output), or None."""
+    # profiles/LATEST_ROLLOUT_CAPTURE names the capture of the committed kernel (written together with it); else the last by name
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2*_rollout_full.txt")))
+    latest = os.path.join(ROOT, "profiles", "LATEST_ROLLOUT_CAPTURE")
+    if os.path.exists(latest):
+        named = os.path.join(ROOT, "profiles", open(latest).read().strip())
+        if os.path.exists(named):
+            files.append(named)
     if not files:
         return None, None
     rd = wr = None
