@@ -9,6 +9,8 @@ same kernel source deviates from the oracle on exactly those samples (tests/test
 window), so for the cfg-noise window the bar is applied to the distribution: >= 98 % of the samples inside the
 tolerance, tight median, bounded worst case.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -377,3 +379,45 @@ def test_a_samples_result_does_not_depend_on_the_batch_around_it(pool):
         out = [x.cpu().numpy() for x in pool.window(parents[pick], actions[pick], target.astype(np.float32), 40, children=1, out_cache=True)]
         for a, b in zip(ref, out):
             assert np.array_equal(a[pick].view(np.uint32), b.view(np.uint32))
+
+
+def test_assembly_pool_equals_the_private_assembly_bit_for_bit(pool, tmp_path):
+    """The shared contact assembly, the helper warps and the reduced barrier set only move work between warps.  A build of
+    the same sources with the pool compiled out (-DSC_SHARE_ASSEMBLY=0: every warp assembles its own tile and nobody helps)
+    must produce the same bits -- states, costs, cost terms, contact caches -- on chained, contact-rich windows."""
+    import subprocess
+    from samcon_b200 import abi, build
+    from samcon_b200.config import Config
+    from samcon_b200.model import Character, SimParams
+    from samcon_b200.pool import GpuSamplePool
+    from samcon_b200.sampling import get_batch_action
+    nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc on this box")
+    lib = str(tmp_path / "libsamcon_b200_private.so")
+    flags = [f for f in build.NVCC_FLAGS if f not in ("-Xptxas", "-v", "-lineinfo")]
+    subprocess.check_call([nvcc, *flags, "-DSC_SHARE_ASSEMBLY=0", "-o", lib, os.path.join(os.path.dirname(abi.LIB_PATH), "samcon_b200.cu")])
+    cfg = Config("walk")
+    ch = Character.from_config(cfg, SimParams(self_collision=True))
+    saved_path, saved_lib = abi.LIB_PATH, abi._lib
+    try:
+        abi.LIB_PATH, abi._lib = lib, None
+        private = GpuSamplePool(ch, 0)
+    finally:
+        abi.LIB_PATH, abi._lib = saved_path, saved_lib
+    try:
+        rng = np.random.default_rng(21)
+        S, E = 5000, 500                                           # 9 tile warps per CTA: the two-barrier instance of the loop
+        parents = np.array([stand(rng, 0.04, 0.3, 0.975) for _ in range(E)], np.float32)
+        caches = None
+        target = stand(rng, 0.03, 0.1, 0.985).astype(np.float32)
+        for w in range(3):
+            actions = get_batch_action(target, S, cfg.values, "uniform", np.random.RandomState(7 + w)).astype(np.float32)
+            a = pool.window(parents, actions, target, 50, parent_cache=caches, out_cache=True)
+            b = private.window(parents, actions, target, 50, parent_cache=caches, out_cache=True)
+            for x, y in zip(a, b):
+                assert np.array_equal(x.cpu().numpy().view(np.uint32), y.cpu().numpy().view(np.uint32))
+            idx, _ = pool.select(a[1], E)
+            parents, caches = pool.gather_rows(a[0], idx.reshape(-1)), pool.gather_rows(a[3], idx.reshape(-1))
+    finally:
+        private.close()
