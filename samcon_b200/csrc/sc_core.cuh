@@ -1205,9 +1205,10 @@ constexpr int COOP_WORDS = 64;          // per CTA, behind the tiles: the pool's
 // works through its own calls, and then takes unclaimed calls of the other tiles until every tile of the CTA is claimed
 // out.  A column only reads its tile (inertias, contact list) and writes its own entries of the packed matrix, so who
 // computes it does not change a bit of the result; the CTA barrier that follows the assembly makes the helpers' writes
-// visible to the owner.  Measured reason: warps with link-link contacts need up to three expensive calls while most need
-// two cheap ones, and 10.7 % of all warp time was spent waiting for them at that barrier
-// (profiles/r2zz_final_phase_stalls.md).  coop: [0,16) ready epoch, [16,32) next call, [32,48) number of calls, per warp.
+// visible to the owner.  Measured reason: a tile needs one to three calls of about 10 / 8.5 / 5.5 k cycles depending on
+// its samples' contact counts, link-link columns cost double, and 10.7 % of all warp time was spent at that barrier
+// waiting for the slowest tile (profiles/r2zz_final_phase_stalls.md; 4-5 % with the pool, profiles/r2_final3_phase_stalls.md).
+// coop: [0,16) ready epoch, [16,32) next call, [32,48) number of calls, per warp; [48,56) the profile build's maxima.
 template <class TT>
 __device__ __forceinline__ void assembly_shared(float *sm, const TT &T, int ncmax, int *coop_, int epoch SC_PROF_ARGS) {
     volatile int *coop = coop_;
